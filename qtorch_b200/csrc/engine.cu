@@ -1,0 +1,780 @@
+// qtorch_b200/csrc/engine.cu -- libqtorch_b200.so: the C ABI declared in include/qtorch_b200.h.
+//
+// Device-resident tensor storage (per-rank pooled: every tensor is exactly 16*4^rank bytes, so one
+// free list per rank is a perfect stream-ordered allocator), the step dispatcher that maps each
+// Network::ContractIndices call (/root/reference/src/Network.h:876) to a kernel family, the grouped
+// micro-step executor, compiled plans (CUDA-graph backed) and the NCCL scalar reduction.
+//
+// No CPU fallback exists: without a CUDA device every compute entry returns QTB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/qtorch_b200.h"
+#include "step.h"
+#include "kernels.cuh"
+#include "gett.cuh"
+#include "reduce.cuh"
+
+using namespace qtb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local std::string g_lastError;
+static int fail(int status, const std::string &msg) { g_lastError = msg; return status; }
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? QTB_ERR_OOM : QTB_ERR_CUDA,              \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+#define ST(call) do { int s_ = (call); if (s_ != QTB_OK) return s_; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel families
+static const unsigned long long MICRO_MAX_UNITS = 1ull << 16;   // 4^8 complex MACs: ~1 us on one SM
+static const int MICRO_MAX_RANK = 7;
+
+struct GettChoice { int cfg; bool swap; };      // cfg: 0 C1/TK16 1 C1/TK4 2 C2/TK16 3 C2/TK4 4 C3/TK16 5 C3/TK4
+
+typedef void (*GettKernel)(const GettParams);
+struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; };
+// C1: 128x64 tile, compute-bound big x big;  C2: 256x16;  C3: 256x8 (N <= 4 padded) -- streaming
+static GettInst g_gett[6] = {
+    {k_gett<4, 2, 4, 4, 16, 3>, 128, 64, 16, 256, GettCfg<4, 2, 4, 4, 16, 3>::SMEM, 1},
+    {k_gett<4, 2, 4, 4, 4, 4>, 128, 64, 4, 256, GettCfg<4, 2, 4, 4, 4, 4>::SMEM, 1},
+    {k_gett<8, 1, 4, 2, 16, 3>, 256, 16, 16, 256, GettCfg<8, 1, 4, 2, 16, 3>::SMEM, 1},
+    {k_gett<8, 1, 4, 2, 4, 4>, 256, 16, 4, 256, GettCfg<8, 1, 4, 2, 4, 4>::SMEM, 1},
+    {k_gett<8, 1, 4, 1, 16, 3>, 256, 8, 16, 256, GettCfg<8, 1, 4, 1, 16, 3>::SMEM, 1},
+    {k_gett<8, 1, 4, 1, 4, 4>, 256, 8, 4, 256, GettCfg<8, 1, 4, 1, 4, 4>::SMEM, 1},
+};
+
+static int ilog2i(unsigned long long v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
+
+// ------------------------------------------------------------------------------------------------
+// geometry: restates the leg bookkeeping of Network::ContractNodes (Network.h:739-769)
+static int make_geom(int rA, int rB, int k, const int *posA, const int *posB, StepGeom &g) {
+    if (rA < 0 || rB < 0 || rA > QTB_MAX_RANK || rB > QTB_MAX_RANK || k < 0 || k > rA || k > rB)
+        return fail(QTB_ERR_INVALID, "bad ranks / shared-leg count");
+    bool usedA[QTB_MAXR] = {false}, usedB[QTB_MAXR] = {false};
+    for (int j = 0; j < k; j++) {
+        const int a = posA[j], b = posB[j];
+        if (a < 0 || a >= rA || b < 0 || b >= rB || usedA[a] || usedB[b] || (j > 0 && a <= posA[j - 1]))
+            return fail(QTB_ERR_INVALID, "bad shared-leg map (pos_a must be strictly increasing, legs distinct)");
+        usedA[a] = usedB[b] = true;
+        g.posA[j] = a; g.posB[j] = b;
+    }
+    g.rA = rA; g.rB = rB; g.k = k; g.nfa = g.nfb = 0;
+    for (int i = 0; i < rA; i++) if (!usedA[i]) g.freeA[g.nfa++] = i;
+    for (int i = 0; i < rB; i++) if (!usedB[i]) g.freeB[g.nfb++] = i;
+    g.rC = g.nfa + g.nfb;
+    if (g.rC > QTB_MAX_RANK) return fail(QTB_ERR_INVALID, "result rank exceeds QTB_MAX_RANK");
+    return QTB_OK;
+}
+
+static void make_devstep(const StepGeom &g, const double2 *A, const double2 *B, double2 *C, int kind, DevStep &st) {
+    memset(&st, 0, sizeof(st));
+    st.A = A; st.B = B; st.C = C;
+    st.rA = g.rA; st.rB = g.rB; st.k = g.k; st.rC = g.rC; st.nfa = g.nfa; st.nfb = g.nfb; st.kind = kind;
+    for (int i = 0; i < g.nfa; i++) st.shFree[i] = 2 * g.freeA[i];
+    for (int i = 0; i < g.nfb; i++) st.shFree[g.nfa + i] = 2 * g.freeB[i];
+    for (int i = 0; i < g.k; i++) {            // summed digit i <-> shared pair k-1-i (Network.h:912-916)
+        st.shSumA[i] = 2 * g.posA[g.k - 1 - i];
+        st.shSumB[i] = 2 * g.posB[g.k - 1 - i];
+    }
+}
+
+static bool force_generic() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_FORCE_GENERIC"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
+static bool disable_micro() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_NO_MICRO"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
+
+static int choose_kind(const StepGeom &g, GettChoice &gc) {
+    const unsigned long long U = g.units();
+    if (!disable_micro() && U <= MICRO_MAX_UNITS && g.rA <= MICRO_MAX_RANK && g.rB <= MICRO_MAX_RANK && g.rC <= MICRO_MAX_RANK)
+        return KIND_MICRO;
+    const int bigFree = std::max(g.nfa, g.nfb), smallFree = std::min(g.nfa, g.nfb);
+    if (!force_generic() && g.rC <= 2 && g.k >= 6) return KIND_REDUCE;       // long sums, <= 16 outputs: split-K
+    if (!force_generic() && bigFree >= 4 && g.k >= 1) {
+        gc.swap = g.nfb > g.nfa;
+        const int tk4 = (g.k == 1) ? 1 : 0;
+        if (smallFree >= 3) gc.cfg = 0 + tk4;
+        else if (smallFree == 2) gc.cfg = 2 + tk4;
+        else gc.cfg = 4 + tk4;
+        return KIND_GETT;
+    }
+    return (g.rC >= 6) ? KIND_THREAD : KIND_WARP;
+}
+
+static void build_gett(const StepGeom &g, const GettChoice &gc, const double2 *A, const double2 *B, double2 *C, GettParams &p) {
+    const GettInst &inst = g_gett[gc.cfg];
+    const int TMB = ilog2i(inst.TM), TNB = ilog2i(inst.TN), TKB = ilog2i(inst.TK);
+    memset(&p, 0, sizeof(p));
+    const bool sw = gc.swap;
+    p.X = sw ? B : A; p.Y = sw ? A : B; p.C = C;
+    const int nfx = sw ? g.nfb : g.nfa, nfy = sw ? g.nfa : g.nfb;
+    const int *freeX = sw ? g.freeB : g.freeA, *freeY = sw ? g.freeA : g.freeB;
+    const int cx0 = sw ? g.nfa : 0, cy0 = sw ? 0 : g.nfa;      // first C digit of the x / y legs
+    p.xbits = 2 * nfx; p.ybits = 2 * nfy; p.kbits = 2 * g.k;
+    for (int i = 0; i < nfx; i++) for (int b = 0; b < 2; b++) { p.shXx[2 * i + b] = 2 * freeX[i] + b; p.shCx[2 * i + b] = 2 * (cx0 + i) + b; }
+    for (int i = 0; i < nfy; i++) for (int b = 0; b < 2; b++) { p.shYy[2 * i + b] = 2 * freeY[i] + b; p.shCy[2 * i + b] = 2 * (cy0 + i) + b; }
+    // summation order is free: put the shared legs that sit lowest in either operand inside the k-chunk
+    int ord[QTB_MAXR];
+    for (int j = 0; j < g.k; j++) ord[j] = j;
+    const int *posX = sw ? g.posB : g.posA, *posY = sw ? g.posA : g.posB;
+    std::stable_sort(ord, ord + g.k, [&](int a, int b) { return std::min(posX[a], posY[a]) < std::min(posX[b], posY[b]); });
+    for (int j = 0; j < g.k; j++) for (int b = 0; b < 2; b++) { p.shXk[2 * j + b] = 2 * posX[ord[j]] + b; p.shYk[2 * j + b] = 2 * posY[ord[j]] + b; }
+    const unsigned long long Mx = 1ull << p.xbits, Ny = 1ull << p.ybits, K = 1ull << p.kbits;
+    p.nyValid = (uint32_t)std::min<unsigned long long>(Ny, inst.TN);
+    p.nyBits = ilog2i(p.nyValid);
+    p.nTilesX = (uint32_t)(Mx / inst.TM);
+    p.nTilesY = (uint32_t)std::max<unsigned long long>(1, Ny / inst.TN);
+    p.nChunks = (uint32_t)(K / inst.TK);
+    // load-order permutations: slot-id bits follow the operand's memory significance
+    struct CB { int shift, coord; };
+    std::vector<CB> v;
+    for (int j = 0; j < TMB; j++) v.push_back({p.shXx[j], j});
+    for (int j = 0; j < TKB; j++) v.push_back({p.shXk[j], TMB + j});
+    std::sort(v.begin(), v.end(), [](const CB &a, const CB &b) { return a.shift < b.shift; });
+    for (size_t j = 0; j < v.size(); j++) p.permX[j] = v[j].coord;
+    v.clear();
+    for (int j = 0; j < p.nyBits; j++) v.push_back({p.shYy[j], j});
+    for (int j = 0; j < TKB; j++) v.push_back({p.shYk[j], TNB + j});
+    std::sort(v.begin(), v.end(), [](const CB &a, const CB &b) { return a.shift < b.shift; });
+    for (size_t j = 0; j < v.size(); j++) p.permY[j] = v[j].coord;
+}
+
+static void build_reduce(const StepGeom &g, const double2 *A, const double2 *B, double2 *C, double2 *partial, ReduceParams &p) {
+    memset(&p, 0, sizeof(p));
+    p.A = A; p.B = B; p.C = C; p.partial = partial;
+    p.kbits = 2 * g.k;
+    p.nTiles = (uint32_t)((1ull << p.kbits) / 256);
+    // tile legs: the two lowest shared legs of A, then the two lowest of B (distinct pairs), so both
+    // operands are read in 256-byte runs; the rest follow in A order
+    std::vector<int> order;
+    auto has = [&](int j) { return std::find(order.begin(), order.end(), j) != order.end(); };
+    std::vector<int> byB(g.k);
+    for (int j = 0; j < g.k; j++) byB[j] = j;
+    std::sort(byB.begin(), byB.end(), [&](int a, int b) { return g.posB[a] < g.posB[b]; });
+    order.push_back(0); order.push_back(1);                           // posA is increasing: pairs 0,1 are lowest in A
+    for (int j = 0; j < g.k && order.size() < 4; j++) if (!has(byB[j])) order.push_back(byB[j]);
+    for (int j = 0; j < g.k; j++) if (!has(j)) order.push_back(j);
+    for (int j = 0; j < g.k; j++) for (int b = 0; b < 2; b++) { p.shA[2 * j + b] = 2 * g.posA[order[j]] + b; p.shB[2 * j + b] = 2 * g.posB[order[j]] + b; }
+    const int NC = 1 << (2 * g.rC);
+    for (int c = 0; c < NC; c++) {
+        uint32_t oa = 0, ob = 0;
+        for (int i = 0; i < g.nfa; i++) oa += (uint32_t)((c >> (2 * i)) & 3) << (2 * g.freeA[i]);
+        for (int i = 0; i < g.nfb; i++) ob += (uint32_t)((c >> (2 * (g.nfa + i))) & 3) << (2 * g.freeB[i]);
+        p.fA[c] = oa; p.fB[c] = ob;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-rank pooled device memory
+struct Pool {
+    std::vector<void *> freeList[QTB_MAX_RANK + 1];
+    std::vector<void *> chunks;                 // cudaMalloc'd blocks owned by this pool
+    uint8_t *slab = nullptr; size_t slabLeft = 0;
+    long long reserved = 0, live = 0, peakLive = 0;
+    static size_t bytes(int rank) { return (size_t)16 << (2 * rank); }
+    static const size_t SLAB = (size_t)8 << 20;   // small tensors (<= 64 KB) are carved from 8 MB slabs
+
+    int alloc(int rank, void **out) {
+        std::vector<void *> &fl = freeList[rank];
+        const size_t b = bytes(rank);
+        if (!fl.empty()) { *out = fl.back(); fl.pop_back(); }
+        else if (b <= (64u << 10)) {
+            const size_t need = std::max<size_t>(b, 256);        // keep 256 B alignment
+            if (slabLeft < need) {
+                void *s = nullptr;
+                CU(cudaMalloc(&s, SLAB));
+                chunks.push_back(s); reserved += SLAB;
+                slab = (uint8_t *)s; slabLeft = SLAB;
+            }
+            *out = slab; slab += need; slabLeft -= need;
+        } else {
+            void *p = nullptr;
+            cudaError_t e = cudaMalloc(&p, b);
+            if (e == cudaErrorMemoryAllocation) {                  // give cached blocks back and retry once
+                cudaGetLastError();
+                trim();
+                e = cudaMalloc(&p, b);
+            }
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? QTB_ERR_OOM : QTB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+            chunks.push_back(p); reserved += (long long)b;
+            *out = p;
+        }
+        live += (long long)b; peakLive = std::max(peakLive, live);
+        return QTB_OK;
+    }
+    void release(int rank, void *p) { freeList[rank].push_back(p); live -= (long long)bytes(rank); }
+    void trim() {       // free cached big blocks (callers have synchronised the stream)
+        cudaDeviceSynchronize();
+        for (int r = 0; r <= QTB_MAX_RANK; r++) {
+            if (bytes(r) <= (64u << 10)) continue;
+            for (void *p : freeList[r]) {
+                cudaFree(p); reserved -= (long long)bytes(r);
+                chunks.erase(std::find(chunks.begin(), chunks.end(), p));
+            }
+            freeList[r].clear();
+        }
+    }
+    void destroy() {
+        for (void *p : chunks) cudaFree(p);
+        chunks.clear();
+        for (auto &f : freeList) f.clear();
+        slab = nullptr; slabLeft = 0; reserved = live = 0;
+    }
+};
+
+struct qtb_tensor_s {
+    double2 *d = nullptr;
+    int rank = 0;
+    bool hasData = false;       // something has been uploaded / contracted into it (possibly still pending)
+    bool pooled = false;        // d belongs to the ctx pool
+};
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (the library must load on boxes without NCCL)
+struct NcclId { char b[QTB_UNIQUE_ID_BYTES]; };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, /*ncclUniqueId by value*/ NcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_ncclMu;
+static int load_nccl() {
+    std::lock_guard<std::mutex> lk(g_ncclMu);
+    if (g_nccl.h) return QTB_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return fail(QTB_ERR_NCCL, "libnccl.so.2 not found");
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(QTB_ERR_NCCL, "NCCL symbols missing");
+    g_nccl.h = h;
+    return QTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct PendingStep { DevStep st; uint32_t level; };
+struct PendingUpload { double2 *dst; size_t payloadOff; uint32_t elems; };
+
+struct TraceRec { cudaEvent_t e0, e1; int rA, rB, k, kernel; };
+
+struct qtb_ctx_s {
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    Pool pool;
+    // staging ring (pinned host mirror + device): micro-batch blobs and small uploads
+    uint8_t *ringHost = nullptr, *ringDev = nullptr;
+    size_t ringSize = (size_t)32 << 20, ringCur = 0;
+    cudaEvent_t ringEvent = nullptr; bool ringEventValid = false;
+    double *scalarPinned = nullptr;
+    uint64_t *zeroOffsetDev = nullptr;          // blobOffsets[0] = 0 for single-blob launches
+    double2 *reduceScratch = nullptr;           // split-K partials: [REDUCE_MAX_BLOCKS][16]
+    // deferred micro work
+    std::vector<PendingStep> pending;
+    std::vector<PendingUpload> pendingUploads;
+    std::vector<uint8_t> payload;
+    std::unordered_map<const void *, uint32_t> producedLevel;     // tensor buffer -> level of the pending step writing it
+    std::vector<std::pair<int, void *>> deferredFrees;            // (rank, ptr) released after the next flush
+    // stats / trace
+    qtb_stats stats{};
+    bool trace = false;
+    std::vector<TraceRec> traceRecs;
+    // NCCL
+    void *comm = nullptr; int nRanks = 1, rank = 0;
+    double *commBuf = nullptr; size_t commBufElems = 0;
+};
+
+static int ensure_device(qtb_ctx *ctx) {
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    return QTB_OK;
+}
+
+static int launch_gett(qtb_ctx *ctx, const GettParams &p, int cfg, cudaStream_t s) {
+    const GettInst &inst = g_gett[cfg];
+    const unsigned nTiles = p.nTilesX * p.nTilesY;
+    const unsigned grid = std::min<unsigned>(nTiles, (unsigned)(ctx->numSMs * inst.occ));
+    inst.fn<<<grid, inst.NT, inst.smem, s>>>(p);
+    CU(cudaGetLastError());
+    ctx->stats.launches++;
+    return QTB_OK;
+}
+
+static const unsigned REDUCE_MAX_BLOCKS = 148 * 8;
+static int launch_reduce(qtb_ctx *ctx, const StepGeom &g, const double2 *A, const double2 *B, double2 *C, cudaStream_t s) {
+    ReduceParams p;
+    build_reduce(g, A, B, C, ctx->reduceScratch, p);
+    const unsigned grid = std::min<unsigned>(p.nTiles, std::min<unsigned>(REDUCE_MAX_BLOCKS, (unsigned)ctx->numSMs * 8));
+    switch (g.rC) {
+        case 0: k_reduce<1><<<grid, 256, 0, s>>>(p); k_reduce_final<1><<<1, 32, 0, s>>>(p.partial, C, grid); break;
+        case 1: k_reduce<4><<<grid, 256, 0, s>>>(p); k_reduce_final<4><<<1, 128, 0, s>>>(p.partial, C, grid); break;
+        default: k_reduce<16><<<grid, 256, 0, s>>>(p); k_reduce_final<16><<<1, 512, 0, s>>>(p.partial, C, grid); break;
+    }
+    CU(cudaGetLastError());
+    ctx->stats.launches += 2;
+    return QTB_OK;
+}
+
+static int launch_generic(qtb_ctx *ctx, const DevStep &st, cudaStream_t s) {
+    const unsigned long long NC = 1ull << (2 * st.rC);
+    if (st.kind == KIND_THREAD) {
+        const unsigned grid = (unsigned)std::min<unsigned long long>((NC + 255) / 256, (unsigned long long)ctx->numSMs * 32);
+        k_step_thread<<<grid, 256, 0, s>>>(st);
+    } else {
+        const unsigned grid = (unsigned)std::min<unsigned long long>((NC + 7) / 8, (unsigned long long)ctx->numSMs * 8);
+        k_step_warp<<<grid, 256, 0, s>>>(st);
+    }
+    CU(cudaGetLastError());
+    ctx->stats.launches++;
+    return QTB_OK;
+}
+
+// ---- micro-batch blob assembly -----------------------------------------------------------------
+// Builds: MicroHeader | levelItemStart | items | steps (copy steps first at level 0) | payload
+static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std::vector<PendingUpload> &ups,
+                               const std::vector<uint8_t> &payload, std::vector<uint8_t> &blob, const uint8_t *devBase) {
+    // level 0 = upload copies and steps with no pending producer; a step's level is
+    // 1 + max(level of the pending op producing each operand)
+    uint32_t nLevels = ups.empty() ? 0 : 1;
+    for (const auto &s : steps) nLevels = std::max(nLevels, s.level + 1);
+    const uint32_t nSteps = (uint32_t)(steps.size() + ups.size());
+    std::vector<std::vector<MicroItem>> perLevel(nLevels);
+    std::vector<DevStep> all(nSteps);
+    uint32_t idx = 0;
+    for (const auto &u : ups) {
+        DevStep &st = all[idx];
+        memset(&st, 0, sizeof(st));
+        st.kind = KIND_COPY; st.C = u.dst; st.A = nullptr;       // A patched below (needs payload offset)
+        st.rC = 0; st.k = 0;
+        // copy steps reuse the item machinery: chunk = block of QTB_MICRO_CHUNK elements
+        const uint32_t nChunks = (u.elems + QTB_MICRO_CHUNK - 1) / QTB_MICRO_CHUNK;
+        for (uint32_t c = 0; c < nChunks; c++) perLevel[0].push_back({idx, c});
+        idx++;
+    }
+    for (const auto &s : steps) {
+        all[idx] = s.st;
+        const uint32_t NC = 1u << (2 * s.st.rC), K = 1u << (2 * s.st.k);
+        const uint32_t nChunks = (NC >= 32 || K < 16) ? (NC + QTB_MICRO_CHUNK - 1) / QTB_MICRO_CHUNK : 1;
+        for (uint32_t c = 0; c < nChunks; c++) perLevel[s.level].push_back({idx, c});
+        idx++;
+    }
+    uint32_t nItems = 0;
+    for (auto &v : perLevel) nItems += (uint32_t)v.size();
+    size_t off = sizeof(MicroHeader) + sizeof(uint32_t) * (nLevels + 1) + sizeof(MicroItem) * nItems;
+    off = (off + 15) & ~(size_t)15;
+    const size_t stepsOff = off;
+    off += sizeof(DevStep) * nSteps;
+    off = (off + 15) & ~(size_t)15;
+    const size_t payloadOff = off;
+    off += payload.size();
+    blob.assign(off, 0);
+    MicroHeader hdr{nLevels, nItems, nSteps, (uint32_t)stepsOff};
+    memcpy(blob.data(), &hdr, sizeof(hdr));
+    uint32_t *lis = reinterpret_cast<uint32_t *>(blob.data() + sizeof(MicroHeader));
+    MicroItem *items = reinterpret_cast<MicroItem *>(lis + nLevels + 1);
+    uint32_t cur = 0;
+    for (uint32_t l = 0; l < nLevels; l++) {
+        lis[l] = cur;
+        for (const auto &it : perLevel[l]) items[cur++] = it;
+    }
+    lis[nLevels] = cur;
+    // patch copy sources (device address of the payload inside the device-side blob)
+    for (size_t i = 0; i < ups.size(); i++) {
+        all[i].A = reinterpret_cast<const double2 *>(devBase + payloadOff + ups[i].payloadOff);
+        // element count travels in the (otherwise unused) B pointer slot
+        all[i].B = reinterpret_cast<const double2 *>((uintptr_t)ups[i].elems);
+    }
+    memcpy(blob.data() + stepsOff, all.data(), sizeof(DevStep) * nSteps);
+    if (!payload.empty()) memcpy(blob.data() + payloadOff, payload.data(), payload.size());
+    return off;
+}
+
+// copy-step aware micro kernel wrapper lives in kernels.cuh (k_micro handles KIND_COPY)
+
+static int ring_reserve(qtb_ctx *ctx, size_t bytes, size_t &off) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > ctx->ringSize) return fail(QTB_ERR_INVALID, "micro batch larger than the staging ring");
+    if (ctx->ringCur + bytes > ctx->ringSize) {
+        // wrap: everything enqueued so far must have consumed its staging bytes
+        if (ctx->ringEventValid) CU(cudaEventSynchronize(ctx->ringEvent));
+        ctx->ringCur = 0;
+    }
+    off = ctx->ringCur;
+    ctx->ringCur += bytes;
+    return QTB_OK;
+}
+
+static int flush_locked(qtb_ctx *ctx) {
+    if (ctx->pending.empty() && ctx->pendingUploads.empty()) {
+        for (auto &f : ctx->deferredFrees) ctx->pool.release(f.first, f.second);
+        ctx->deferredFrees.clear();
+        return QTB_OK;
+    }
+    ST(ensure_device(ctx));
+    std::vector<uint8_t> blob;
+    // two passes: size first (device base unknown until the ring slot is known)
+    size_t need = build_micro_blob(ctx->pending, ctx->pendingUploads, ctx->payload, blob, nullptr);
+    size_t off = 0;
+    ST(ring_reserve(ctx, need, off));
+    build_micro_blob(ctx->pending, ctx->pendingUploads, ctx->payload, blob, ctx->ringDev + off);
+    memcpy(ctx->ringHost + off, blob.data(), blob.size());
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
+    CU(cudaMemcpyAsync(ctx->ringDev + off, ctx->ringHost + off, blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.bytes_h2d += (long long)blob.size();
+    k_micro<<<1, QTB_MICRO_THREADS, 0, ctx->stream>>>(ctx->ringDev + off, ctx->zeroOffsetDev);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ringEvent, ctx->stream));
+    ctx->ringEventValid = true;
+    if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, 0, 0, (int)ctx->pending.size(), KIND_MICRO}); }
+    ctx->stats.launches++;
+    ctx->stats.micro_steps += (long long)ctx->pending.size();
+    ctx->pending.clear(); ctx->pendingUploads.clear(); ctx->payload.clear(); ctx->producedLevel.clear();
+    for (auto &f : ctx->deferredFrees) ctx->pool.release(f.first, f.second);
+    ctx->deferredFrees.clear();
+    return QTB_OK;
+}
+
+static int ensure_buffer(qtb_ctx *ctx, qtb_tensor t) {
+    if (t->d) return QTB_OK;
+    void *p = nullptr;
+    ST(ctx->pool.alloc(t->rank, &p));
+    t->d = (double2 *)p; t->pooled = true;
+    return QTB_OK;
+}
+
+// enqueue one non-micro step on a stream (shared by the eager path and compiled plans)
+static int enqueue_big(qtb_ctx *ctx, const StepGeom &g, int kind, const GettChoice &gc, const double2 *A, const double2 *B,
+                       double2 *C, cudaStream_t s) {
+    if (kind == KIND_GETT) {
+        GettParams p;
+        build_gett(g, gc, A, B, C, p);
+        return launch_gett(ctx, p, gc.cfg, s);
+    }
+    if (kind == KIND_REDUCE) return launch_reduce(ctx, g, A, B, C, s);
+    DevStep st;
+    make_devstep(g, A, B, C, kind, st);
+    return launch_generic(ctx, st, s);
+}
+
+// ================================================================================================
+// C ABI
+extern "C" {
+
+int qtb_abi_version(void) { return QTB_ABI_VERSION; }
+
+const char *qtb_status_string(int s) {
+    switch (s) {
+        case QTB_OK: return "ok";
+        case QTB_ERR_NO_DEVICE: return "no CUDA device (qtorch_b200 has no CPU fallback)";
+        case QTB_ERR_INVALID: return "invalid argument";
+        case QTB_ERR_EMPTY_INPUT: return "operand has no data";
+        case QTB_ERR_OOM: return "out of device memory";
+        case QTB_ERR_CUDA: return "CUDA error";
+        case QTB_ERR_NCCL: return "NCCL error";
+        case QTB_ERR_UNSUPPORTED: return "unsupported";
+    }
+    return "unknown status";
+}
+const char *qtb_last_error(void) { return g_lastError.c_str(); }
+
+int qtb_device_count(int *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); if (count) *count = 0; return fail(QTB_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    if (count) *count = n;
+    return QTB_OK;
+}
+
+int qtb_ctx_create(int device, qtb_ctx **out) {
+    if (!out) return fail(QTB_ERR_INVALID, "null out");
+    *out = nullptr;
+    int n = 0;
+    ST(qtb_device_count(&n));
+    if (device < 0 || device >= n) return fail(QTB_ERR_INVALID, "device index out of range");
+    qtb_ctx *ctx = new qtb_ctx_s();
+    ctx->device = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { delete ctx; return fail(QTB_ERR_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only"); }
+    ctx->numSMs = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost((void **)&ctx->ringHost, ctx->ringSize));
+    CU(cudaMalloc((void **)&ctx->ringDev, ctx->ringSize));
+    CU(cudaMallocHost((void **)&ctx->scalarPinned, 64));
+    CU(cudaMalloc((void **)&ctx->zeroOffsetDev, 8));
+    CU(cudaMalloc((void **)&ctx->reduceScratch, (size_t)REDUCE_MAX_BLOCKS * 16 * sizeof(double2)));
+    CU(cudaMemset(ctx->zeroOffsetDev, 0, 8));
+    CU(cudaEventCreateWithFlags(&ctx->ringEvent, cudaEventDisableTiming));
+    for (auto &inst : g_gett) {
+        CU(cudaFuncSetAttribute(inst.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inst.smem));
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inst.fn, inst.NT, inst.smem));
+        inst.occ = std::max(1, occ);
+    }
+    CU(cudaDeviceSynchronize());
+    *out = ctx;
+    return QTB_OK;
+}
+
+int qtb_ctx_destroy(qtb_ctx *ctx) {
+    if (!ctx) return QTB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->commBuf) cudaFree(ctx->commBuf);
+    for (auto &t : ctx->traceRecs) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    ctx->pool.destroy();
+    cudaFreeHost(ctx->ringHost); cudaFree(ctx->ringDev); cudaFreeHost(ctx->scalarPinned); cudaFree(ctx->zeroOffsetDev); cudaFree(ctx->reduceScratch);
+    cudaEventDestroy(ctx->ringEvent);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return QTB_OK;
+}
+
+int qtb_ctx_flush(qtb_ctx *ctx) {
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return flush_locked(ctx);
+}
+int qtb_ctx_sync(qtb_ctx *ctx) {
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(flush_locked(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return QTB_OK;
+}
+void *qtb_ctx_stream(qtb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int qtb_tensor_alloc(qtb_ctx *ctx, int rank, qtb_tensor *out) {
+    if (!ctx || !out) return fail(QTB_ERR_INVALID, "null argument");
+    if (rank < 0 || rank > QTB_MAX_RANK) return fail(QTB_ERR_INVALID, "rank out of range");
+    qtb_tensor t = new qtb_tensor_s();
+    t->rank = rank;                      // device memory is bound lazily (first upload / first use as an output)
+    *out = t;
+    return QTB_OK;
+}
+
+int qtb_tensor_free(qtb_ctx *ctx, qtb_tensor t) {
+    if (!t) return QTB_OK;
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (t->d && t->pooled) {
+        // stream-ordered: deferred micro-steps may still reference the buffer, so it returns to the
+        // pool right after the next flush is enqueued
+        if (ctx->pending.empty() && ctx->pendingUploads.empty()) ctx->pool.release(t->rank, t->d);
+        else ctx->deferredFrees.push_back({t->rank, (void *)t->d});
+    }
+    delete t;
+    return QTB_OK;
+}
+
+int qtb_tensor_rank(qtb_tensor t) { return t ? t->rank : -1; }
+void *qtb_tensor_device_ptr(qtb_tensor t) { return t ? (void *)t->d : nullptr; }
+
+int qtb_tensor_upload(qtb_ctx *ctx, qtb_tensor t, const double *host) {
+    if (!ctx || !t || !host) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    ST(ensure_buffer(ctx, t));
+    const size_t bytes = Pool::bytes(t->rank);
+    if (t->rank <= 5 && !disable_micro()) {
+        // rides in the next grouped launch as a level-0 copy item (one H2D for the whole batch)
+        if (ctx->payload.size() + bytes > ((size_t)8 << 20) || ctx->pending.size() + ctx->pendingUploads.size() >= 8192) ST(flush_locked(ctx));
+        const size_t off = ctx->payload.size();
+        ctx->payload.resize(off + bytes);
+        memcpy(ctx->payload.data() + off, host, bytes);
+        ctx->pendingUploads.push_back({t->d, off, (uint32_t)(bytes / 16)});
+        ctx->producedLevel[t->d] = 0;
+    } else {
+        ST(flush_locked(ctx));
+        CU(cudaMemcpyAsync(t->d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));       // pageable source: the caller may reuse it on return
+    }
+    ctx->stats.bytes_h2d += (long long)bytes;
+    t->hasData = true;
+    return QTB_OK;
+}
+
+int qtb_tensor_download(qtb_ctx *ctx, qtb_tensor t, double *host) {
+    if (!ctx || !t || !host) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!t->hasData || !t->d) return fail(QTB_ERR_EMPTY_INPUT, "tensor has no data");
+    ST(flush_locked(ctx));
+    const size_t bytes = Pool::bytes(t->rank);
+    CU(cudaMemcpyAsync(host, t->d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.bytes_d2h += (long long)bytes;
+    return QTB_OK;
+}
+
+int qtb_read_scalar(qtb_ctx *ctx, qtb_tensor t, double out[2]) {
+    if (!ctx || !t || !out) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!t->hasData || !t->d) return fail(QTB_ERR_EMPTY_INPUT, "tensor has no data");
+    ST(flush_locked(ctx));
+    CU(cudaMemcpyAsync(ctx->scalarPinned, t->d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    out[0] = ctx->scalarPinned[0]; out[1] = ctx->scalarPinned[1];
+    ctx->stats.bytes_d2h += 16;
+    return QTB_OK;
+}
+
+int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos_a, const int *pos_b, qtb_tensor c) {
+    if (!ctx || !a || !b || !c) return fail(QTB_ERR_INVALID, "null argument");
+    if (k > 0 && (!pos_a || !pos_b)) return fail(QTB_ERR_INVALID, "null leg map");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!a->hasData || !b->hasData || !a->d || !b->d) return fail(QTB_ERR_EMPTY_INPUT, "operand has no data (Network.h:938-940)");
+    StepGeom g;
+    ST(make_geom(a->rank, b->rank, k, pos_a, pos_b, g));
+    if (g.rC != c->rank) return fail(QTB_ERR_INVALID, "rank(C) != rank(A)+rank(B)-2k");
+    if (c == a || c == b) return fail(QTB_ERR_INVALID, "output aliases an operand");
+    ST(ensure_device(ctx));
+    ST(ensure_buffer(ctx, c));
+    GettChoice gc{0, false};
+    const int kind = choose_kind(g, gc);
+    ctx->stats.steps++;
+    ctx->stats.units += (long long)g.units();
+    if (kind == KIND_MICRO) {
+        PendingStep ps;
+        make_devstep(g, a->d, b->d, c->d, KIND_MICRO, ps.st);
+        uint32_t lvl = 0;
+        auto ia = ctx->producedLevel.find(a->d);
+        if (ia != ctx->producedLevel.end()) lvl = std::max(lvl, ia->second + 1);
+        auto ib = ctx->producedLevel.find(b->d);
+        if (ib != ctx->producedLevel.end()) lvl = std::max(lvl, ib->second + 1);
+        ps.level = lvl;
+        ctx->pending.push_back(ps);
+        ctx->producedLevel[c->d] = lvl;
+        if (ctx->pending.size() >= 8192) ST(flush_locked(ctx));
+    } else {
+        ST(flush_locked(ctx));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
+        ST(enqueue_big(ctx, g, kind, gc, a->d, b->d, c->d, ctx->stream));
+        if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, g.rA, g.rB, g.k, kind}); }
+    }
+    c->hasData = true;
+    return QTB_OK;
+}
+
+// ---- stats / trace ------------------------------------------------------------------------------
+int qtb_ctx_stats(qtb_ctx *ctx, qtb_stats *out) {
+    if (!ctx || !out) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = ctx->stats;
+    out->pool_bytes_reserved = ctx->pool.reserved;
+    out->pool_bytes_peak_live = ctx->pool.peakLive;
+    return QTB_OK;
+}
+int qtb_ctx_reset_stats(qtb_ctx *ctx) {
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stats = qtb_stats{};
+    return QTB_OK;
+}
+int qtb_ctx_trace_enable(qtb_ctx *ctx, int on) {
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->trace = on != 0;
+    return QTB_OK;
+}
+int qtb_ctx_trace_read(qtb_ctx *ctx, qtb_step_trace *out, int maxEntries, int *n) {
+    if (!ctx || !n) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(flush_locked(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int cnt = 0;
+    for (auto &t : ctx->traceRecs) {
+        if (out && cnt < maxEntries) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, t.e0, t.e1));
+            out[cnt].rank_a = t.rA; out[cnt].rank_b = t.rB; out[cnt].k = t.k; out[cnt].kernel = t.kernel; out[cnt].ms = ms;
+        }
+        cnt++;
+        cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+    }
+    ctx->traceRecs.clear();
+    *n = std::min(cnt, maxEntries);
+    return QTB_OK;
+}
+
+// ---- NCCL ------------------------------------------------------------------------------------------
+int qtb_comm_unique_id(char id[QTB_UNIQUE_ID_BYTES]) {
+    ST(load_nccl());
+    NcclId nid; memset(&nid, 0, sizeof(nid));
+    int r = g_nccl.GetUniqueId(&nid);
+    if (r != 0) return fail(QTB_ERR_NCCL, std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    memcpy(id, nid.b, QTB_UNIQUE_ID_BYTES);
+    return QTB_OK;
+}
+int qtb_comm_init(qtb_ctx *ctx, int nRanks, int rank, const char id[QTB_UNIQUE_ID_BYTES]) {
+    if (!ctx || !id) return fail(QTB_ERR_INVALID, "null argument");
+    ST(load_nccl());
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    NcclId nid; memcpy(nid.b, id, QTB_UNIQUE_ID_BYTES);
+    int r = g_nccl.CommInitRank(&ctx->comm, nRanks, nid, rank);
+    if (r != 0) return fail(QTB_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    ctx->nRanks = nRanks; ctx->rank = rank;
+    return QTB_OK;
+}
+int qtb_comm_destroy(qtb_ctx *ctx) {
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    return QTB_OK;
+}
+int qtb_allreduce_sum(qtb_ctx *ctx, double *host, int nComplex) {
+    if (!ctx || !host || nComplex < 0) return fail(QTB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->comm) return fail(QTB_ERR_NCCL, "communicator not initialised (qtb_comm_init)");
+    ST(ensure_device(ctx));
+    ST(flush_locked(ctx));
+    const size_t n = (size_t)nComplex * 2;
+    if (n > ctx->commBufElems) {
+        if (ctx->commBuf) CU(cudaFree(ctx->commBuf));
+        CU(cudaMalloc((void **)&ctx->commBuf, std::max<size_t>(n, 1024) * 8));
+        ctx->commBufElems = std::max<size_t>(n, 1024);
+    }
+    CU(cudaMemcpyAsync(ctx->commBuf, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int r = g_nccl.AllReduce(ctx->commBuf, ctx->commBuf, n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+    if (r != 0) return fail(QTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    CU(cudaMemcpyAsync(host, ctx->commBuf, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return QTB_OK;
+}
+
+}  // extern "C"
+
+#include "plan.inl"

@@ -1,0 +1,184 @@
+// qtorch_b200/csrc/kernels.cuh -- sm_100a kernels for the latency- and bandwidth-bound step classes.
+//
+//   k_step_thread  one thread per output element, sequential sum over the K = 4^k shared index
+//                  (mid-size steps; coalesced along C / A's low free legs)
+//   k_step_warp    one warp per output element, lanes stride over K, shuffle reduction
+//                  (few outputs, long sums: the rank-0/1 results that close a network)
+//   k_micro        the grouped micro-step executor: ONE launch runs a whole dependency-levelled
+//                  list of tiny steps (replaces thousands of ContractNodes-sized launches; the
+//                  GHZ-1000 plan is 2 999 steps of <= 4^5 MACs, /root/reference/src/Network.h:876)
+//
+// All of them compute  C[c] = sum_s A[offA(c,s)] * B[offB(c,s)]  (Network.h:892-935) with FP64 FMAs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "step.h"
+
+namespace qtb {
+
+__device__ __forceinline__ void cmac(double &cr, double &ci, const double2 a, const double2 b) {
+    cr = fma(a.x, b.x, cr);
+    cr = fma(-a.y, b.y, cr);
+    ci = fma(a.x, b.y, ci);
+    ci = fma(a.y, b.x, ci);
+}
+
+// element offsets contributed by output index c
+__device__ __forceinline__ void free_offsets(const DevStep &st, uint64_t c, uint64_t &oa, uint64_t &ob) {
+    oa = 0; ob = 0;
+    const int nfa = st.nfa, rC = st.rC;
+    for (int i = 0; i < nfa; i++) oa += ((c >> (2 * i)) & 3ull) << st.shFree[i];
+    for (int i = nfa; i < rC; i++) ob += ((c >> (2 * i)) & 3ull) << st.shFree[i];
+}
+// element offsets contributed by summed index s
+__device__ __forceinline__ void sum_offsets(const DevStep &st, uint64_t s, uint64_t &oa, uint64_t &ob) {
+    oa = 0; ob = 0;
+    const int k = st.k;
+    for (int i = 0; i < k; i++) {
+        const uint64_t d = (s >> (2 * i)) & 3ull;
+        oa += d << st.shSumA[i];
+        ob += d << st.shSumB[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_step_thread(const DevStep st) {
+    const uint64_t NC = 1ull << (2 * st.rC), K = 1ull << (2 * st.k);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < NC; c += stride) {
+        uint64_t ba, bb;
+        free_offsets(st, c, ba, bb);
+        const double2 *__restrict__ pa = st.A + ba;
+        const double2 *__restrict__ pb = st.B + bb;
+        double cr = 0.0, ci = 0.0;
+        if (st.k <= 3) {
+            // small K: offsets of the <= 64 summed terms are cheap to rebuild digit by digit
+            for (uint64_t s = 0; s < K; s++) {
+                uint64_t oa, ob;
+                sum_offsets(st, s, oa, ob);
+                cmac(cr, ci, pa[oa], pb[ob]);
+            }
+        } else {
+            // long sums: walk the low three summed digits in an inner block of 64
+            for (uint64_t s1 = 0; s1 < K; s1 += 64) {
+                uint64_t oa1, ob1;
+                sum_offsets(st, s1, oa1, ob1);
+#pragma unroll 4
+                for (uint32_t s0 = 0; s0 < 64; s0++) {
+                    const uint64_t oa = oa1 + ((uint64_t)(s0 & 3) << st.shSumA[0]) + ((uint64_t)((s0 >> 2) & 3) << st.shSumA[1]) +
+                                        ((uint64_t)(s0 >> 4) << st.shSumA[2]);
+                    const uint64_t ob = ob1 + ((uint64_t)(s0 & 3) << st.shSumB[0]) + ((uint64_t)((s0 >> 2) & 3) << st.shSumB[1]) +
+                                        ((uint64_t)(s0 >> 4) << st.shSumB[2]);
+                    cmac(cr, ci, pa[oa], pb[ob]);
+                }
+            }
+        }
+        st.C[c] = make_double2(cr, ci);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_step_warp(const DevStep st) {
+    const uint64_t NC = 1ull << (2 * st.rC), K = 1ull << (2 * st.k);
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t c = warp; c < NC; c += nwarps) {
+        uint64_t ba, bb;
+        free_offsets(st, c, ba, bb);
+        double cr = 0.0, ci = 0.0;
+        for (uint64_t s = lane; s < K; s += 32) {
+            uint64_t oa, ob;
+            sum_offsets(st, s, oa, ob);
+            cmac(cr, ci, st.A[ba + oa], st.B[bb + ob]);
+        }
+        cr = warp_sum(cr); ci = warp_sum(ci);
+        if (lane == 0) st.C[c] = make_double2(cr, ci);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grouped micro-step executor.
+//
+// blob layout (built by the host, one per independent plan; blockIdx.x selects the blob):
+//   MicroHeader | uint32 levelItemStart[nLevels+1] | MicroItem items[nItems] | DevStep steps[nSteps]
+// Steps of one dependency level are independent; a level's work is cut into items of
+// QTB_MICRO_CHUNK outputs which the CTA's warps share; __syncthreads() separates levels (it also
+// orders the global-memory writes of one level before the reads of the next, CTA scope).
+#define QTB_MICRO_CHUNK 128
+#define QTB_MICRO_THREADS 1024
+
+struct MicroHeader { uint32_t nLevels, nItems, nSteps, stepsOffset; };
+struct MicroItem { uint32_t step; uint32_t chunk; };
+
+__global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *__restrict__ blobBase,
+                                                                  const uint64_t *__restrict__ blobOffsets) {
+    const uint8_t *blob = blobBase + blobOffsets[blockIdx.x];
+    const MicroHeader hdr = *reinterpret_cast<const MicroHeader *>(blob);
+    const uint32_t *lis = reinterpret_cast<const uint32_t *>(blob + sizeof(MicroHeader));
+    const MicroItem *items = reinterpret_cast<const MicroItem *>(lis + hdr.nLevels + 1);
+    const DevStep *steps = reinterpret_cast<const DevStep *>(blob + hdr.stepsOffset);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+    for (uint32_t lvl = 0; lvl < hdr.nLevels; lvl++) {
+        const uint32_t i0 = lis[lvl], i1 = lis[lvl + 1];
+        for (uint32_t it = i0 + warp; it < i1; it += nw) {
+            const MicroItem item = items[it];
+            const DevStep &st = steps[item.step];
+            const uint32_t NC = 1u << (2 * st.rC), K = 1u << (2 * st.k);
+            // plain (coherent) loads: operands may have been written earlier in this launch
+            const double2 *A = st.A;
+            const double2 *B = st.B;
+            if (st.kind == KIND_COPY) {
+                // staged upload: payload inside this blob -> the tensor's pooled buffer
+                // (element count travels in the B slot)
+                const uint32_t elems = (uint32_t)reinterpret_cast<uintptr_t>(B);
+#pragma unroll
+                for (int j = 0; j < QTB_MICRO_CHUNK / 32; j++) {
+                    const uint32_t e = item.chunk * QTB_MICRO_CHUNK + j * 32 + lane;
+                    if (e < elems) st.C[e] = A[e];
+                }
+            } else if (NC >= 32 || K < 16) {
+                // lanes over outputs
+#pragma unroll 1
+                for (int j = 0; j < QTB_MICRO_CHUNK / 32; j++) {
+                    const uint32_t c = item.chunk * QTB_MICRO_CHUNK + j * 32 + lane;
+                    if (c < NC) {
+                        uint64_t ba, bb;
+                        free_offsets(st, c, ba, bb);
+                        double cr = 0.0, ci = 0.0;
+                        for (uint32_t s = 0; s < K; s++) {
+                            uint64_t oa, ob;
+                            sum_offsets(st, s, oa, ob);
+                            cmac(cr, ci, A[ba + oa], B[bb + ob]);
+                        }
+                        st.C[c] = make_double2(cr, ci);
+                    }
+                }
+            } else {
+                // few outputs, longer sums: lanes over the summed index
+                for (uint32_t c = 0; c < NC; c++) {
+                    uint64_t ba, bb;
+                    free_offsets(st, c, ba, bb);
+                    double cr = 0.0, ci = 0.0;
+                    for (uint32_t s = lane; s < K; s += 32) {
+                        uint64_t oa, ob;
+                        sum_offsets(st, s, oa, ob);
+                        cmac(cr, ci, A[ba + oa], B[bb + ob]);
+                    }
+                    cr = warp_sum(cr); ci = warp_sum(ci);
+                    if (lane == 0) st.C[c] = make_double2(cr, ci);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace qtb

@@ -1,0 +1,288 @@
+// qtorch_b200/csrc/plan.inl -- compiled contraction plans (included at the end of engine.cu).
+//
+// A plan is the list of (A, B, shared legs) steps that a sequence of Network::ContractNodes calls
+// produces (/root/reference/src/Network.h:715-864; the reference's own record of it is the list of
+// mCreatedFrom pairs, Network.h:853-857).  Compiling it once assigns pooled device buffers with
+// liveness-based reuse, pre-builds the grouped micro-step blobs and captures the launch sequence in
+// a CUDA graph, so repeated evaluations (QAOA terms per COBYLA iteration, slices) cost a handful of
+// launches each.
+
+struct PlanSeg {
+    bool micro = false;
+    uint32_t microIndex = 0;      // index into segOffsetsDev
+    int nSteps = 0;
+    StepGeom g; int kind = 0; GettChoice gc{0, false};
+    const double2 *A = nullptr, *B = nullptr; double2 *C = nullptr;
+};
+
+struct qtb_plan_s {
+    Pool pool;
+    int nInputs = 0;
+    std::vector<int> inputRanks;
+    std::vector<double2 *> inputDev;
+    std::vector<size_t> inputBlobOff;       // (size_t)-1 for big inputs living in the pool
+    uint8_t *inBlobHost = nullptr, *inBlobDev = nullptr; size_t inBlobBytes = 0;
+    cudaEvent_t inEvent = nullptr; bool inEventValid = false;
+    uint8_t *microBlobDev = nullptr; uint64_t *segOffsetsDev = nullptr; size_t microBlobBytes = 0;
+    std::vector<PlanSeg> segs;
+    double2 *outDev = nullptr; int outRank = 0;
+    long long units = 0; int nSteps = 0, nMicroSteps = 0; int launches = 0;
+    cudaGraphExec_t graph = nullptr; bool graphTried = false;
+};
+
+static bool plan_graphs_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_PLAN_GRAPH"); v = (e && !atoi(e)) ? 0 : 1; }
+    return v == 1;
+}
+
+static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s) {
+    for (const PlanSeg &sg : pl->segs) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, s)); }
+        if (sg.micro) {
+            k_micro<<<1, QTB_MICRO_THREADS, 0, s>>>(pl->microBlobDev, pl->segOffsetsDev + sg.microIndex);
+            CU(cudaGetLastError());
+            ctx->stats.launches++;
+        } else {
+            ST(enqueue_big(ctx, sg.g, sg.kind, sg.gc, sg.A, sg.B, sg.C, s));
+        }
+        if (ctx->trace) {
+            CU(cudaEventRecord(e1, s));
+            ctx->traceRecs.push_back({e0, e1, sg.micro ? 0 : sg.g.rA, sg.micro ? 0 : sg.g.rB, sg.micro ? sg.nSteps : sg.g.k, sg.micro ? KIND_MICRO : sg.kind});
+        }
+    }
+    return QTB_OK;
+}
+
+extern "C" {
+
+int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps, const qtb_plan_step *steps, qtb_plan **out) {
+    if (!ctx || !out || nInputs < 0 || nSteps < 1 || (nInputs > 0 && !inputRanks) || !steps) return fail(QTB_ERR_INVALID, "bad plan arguments");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    const int nT = nInputs + nSteps;
+    std::vector<int> rank(nT, -1);
+    std::vector<char> consumed(nT, 0);
+    for (int i = 0; i < nInputs; i++) {
+        if (inputRanks[i] < 0 || inputRanks[i] > QTB_MAX_RANK) return fail(QTB_ERR_INVALID, "input rank out of range");
+        rank[i] = inputRanks[i];
+    }
+    // ---- validate + geometry
+    std::vector<StepGeom> geoms(nSteps);
+    for (int i = 0; i < nSteps; i++) {
+        const qtb_plan_step &s = steps[i];
+        if (s.a < 0 || s.b < 0 || s.a >= nInputs + i || s.b >= nInputs + i || s.a == s.b) return fail(QTB_ERR_INVALID, "plan step references an unknown tensor");
+        if (consumed[s.a] || consumed[s.b]) return fail(QTB_ERR_EMPTY_INPUT, "plan step re-uses an already contracted tensor (Network.h:719-723)");
+        int pa[QTB_MAXR], pb[QTB_MAXR];
+        if (s.k < 0 || s.k > QTB_MAXR) return fail(QTB_ERR_INVALID, "bad shared-leg count");
+        for (int j = 0; j < s.k; j++) { pa[j] = s.pos_a[j]; pb[j] = s.pos_b[j]; }
+        ST(make_geom(rank[s.a], rank[s.b], s.k, pa, pb, geoms[i]));
+        rank[nInputs + i] = geoms[i].rC;
+        consumed[s.a] = consumed[s.b] = 1;
+    }
+    qtb_plan *pl = new qtb_plan_s();
+    auto bail = [&](int st) { pl->pool.destroy(); if (pl->inBlobHost) cudaFreeHost(pl->inBlobHost); if (pl->inBlobDev) cudaFree(pl->inBlobDev);
+                              if (pl->microBlobDev) cudaFree(pl->microBlobDev); if (pl->segOffsetsDev) cudaFree(pl->segOffsetsDev); delete pl; return st; };
+    pl->nInputs = nInputs; pl->inputRanks.assign(inputRanks, inputRanks + nInputs);
+    pl->inputDev.assign(nInputs, nullptr); pl->inputBlobOff.assign(nInputs, (size_t)-1);
+    // ---- inputs: small ones share one staging blob (one H2D per evaluation)
+    size_t blobBytes = 0;
+    for (int i = 0; i < nInputs; i++) {
+        if (rank[i] <= 5) { pl->inputBlobOff[i] = blobBytes; blobBytes += std::max<size_t>(Pool::bytes(rank[i]), 256); }
+    }
+    pl->inBlobBytes = blobBytes;
+    if (blobBytes) {
+        if (cudaMallocHost((void **)&pl->inBlobHost, blobBytes) != cudaSuccess || cudaMalloc((void **)&pl->inBlobDev, blobBytes) != cudaSuccess)
+            return bail(fail(QTB_ERR_OOM, "plan input staging allocation failed"));
+    }
+    std::vector<double2 *> dev(nT, nullptr);
+    for (int i = 0; i < nInputs; i++) {
+        if (pl->inputBlobOff[i] != (size_t)-1) dev[i] = (double2 *)(pl->inBlobDev + pl->inputBlobOff[i]);
+        else { void *p = nullptr; int st = pl->pool.alloc(rank[i], &p); if (st != QTB_OK) return bail(st); dev[i] = (double2 *)p; }
+        pl->inputDev[i] = dev[i];
+    }
+    // ---- walk the steps: buffers, kernel families, micro segments
+    std::vector<std::vector<uint8_t>> microBlobs;
+    std::vector<PendingStep> cur;
+    std::vector<uint32_t> levelOf(nT, 0);           // level (+1) of the pending micro-step that produces a tensor, 0 = ready
+    std::vector<std::pair<int, void *>> deferred;
+    auto closeMicro = [&]() {
+        if (cur.empty()) return;
+        PlanSeg sg; sg.micro = true; sg.microIndex = (uint32_t)microBlobs.size(); sg.nSteps = (int)cur.size();
+        pl->segs.push_back(sg);
+        microBlobs.emplace_back();                   // assembled once all device addresses are known (below)
+        // keep the raw steps: stash them in the blob vector as bytes for now
+        microBlobs.back().resize(cur.size() * sizeof(PendingStep));
+        memcpy(microBlobs.back().data(), cur.data(), cur.size() * sizeof(PendingStep));
+        cur.clear();
+        std::fill(levelOf.begin(), levelOf.end(), 0);
+        for (auto &f : deferred) pl->pool.release(f.first, f.second);
+        deferred.clear();
+    };
+    for (int i = 0; i < nSteps; i++) {
+        const qtb_plan_step &s = steps[i];
+        const StepGeom &g = geoms[i];
+        GettChoice gc{0, false};
+        const int kind = choose_kind(g, gc);
+        void *cp = nullptr;
+        { int st = pl->pool.alloc(g.rC, &cp); if (st != QTB_OK) return bail(st); }
+        dev[nInputs + i] = (double2 *)cp;
+        pl->units += (long long)g.units();
+        if (kind == KIND_MICRO) {
+            PendingStep ps;
+            make_devstep(g, dev[s.a], dev[s.b], dev[nInputs + i], KIND_MICRO, ps.st);
+            ps.level = std::max(levelOf[s.a], levelOf[s.b]);
+            cur.push_back(ps);
+            levelOf[nInputs + i] = ps.level + 1;
+            pl->nMicroSteps++;
+            if (s.a >= nInputs) deferred.push_back({rank[s.a], (void *)dev[s.a]});
+            if (s.b >= nInputs) deferred.push_back({rank[s.b], (void *)dev[s.b]});
+        } else {
+            closeMicro();
+            PlanSeg sg; sg.micro = false; sg.g = g; sg.kind = kind; sg.gc = gc; sg.nSteps = 1;
+            sg.A = dev[s.a]; sg.B = dev[s.b]; sg.C = dev[nInputs + i];
+            pl->segs.push_back(sg);
+            if (s.a >= nInputs) pl->pool.release(rank[s.a], dev[s.a]);
+            if (s.b >= nInputs) pl->pool.release(rank[s.b], dev[s.b]);
+        }
+    }
+    closeMicro();
+    pl->nSteps = nSteps;
+    pl->outDev = dev[nT - 1]; pl->outRank = rank[nT - 1];
+    pl->launches = 0;
+    for (const PlanSeg &sg : pl->segs) pl->launches += (!sg.micro && sg.kind == KIND_REDUCE) ? 2 : 1;
+    // ---- assemble micro blobs into one device allocation
+    if (!microBlobs.empty()) {
+        std::vector<uint64_t> offs(microBlobs.size());
+        std::vector<std::vector<uint8_t>> built(microBlobs.size());
+        size_t total = 0;
+        for (size_t m = 0; m < microBlobs.size(); m++) {
+            std::vector<PendingStep> st(microBlobs[m].size() / sizeof(PendingStep));
+            memcpy(st.data(), microBlobs[m].data(), microBlobs[m].size());
+            build_micro_blob(st, {}, {}, built[m], nullptr);
+            offs[m] = total;
+            total += (built[m].size() + 255) & ~(size_t)255;
+        }
+        pl->microBlobBytes = total;
+        if (cudaMalloc((void **)&pl->microBlobDev, total) != cudaSuccess || cudaMalloc((void **)&pl->segOffsetsDev, offs.size() * 8) != cudaSuccess)
+            return bail(fail(QTB_ERR_OOM, "plan blob allocation failed"));
+        std::vector<uint8_t> hostAll(total, 0);
+        for (size_t m = 0; m < built.size(); m++) memcpy(hostAll.data() + offs[m], built[m].data(), built[m].size());
+        if (cudaMemcpy(pl->microBlobDev, hostAll.data(), total, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(pl->segOffsetsDev, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(QTB_ERR_CUDA, "plan blob upload failed"));
+    }
+    if (cudaEventCreateWithFlags(&pl->inEvent, cudaEventDisableTiming) != cudaSuccess) return bail(fail(QTB_ERR_CUDA, "event"));
+    *out = pl;
+    return QTB_OK;
+}
+
+int qtb_plan_destroy(qtb_ctx *ctx, qtb_plan *pl) {
+    if (!pl) return QTB_OK;
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (pl->graph) cudaGraphExecDestroy(pl->graph);
+    pl->pool.destroy();
+    if (pl->inBlobHost) cudaFreeHost(pl->inBlobHost);
+    if (pl->inBlobDev) cudaFree(pl->inBlobDev);
+    if (pl->microBlobDev) cudaFree(pl->microBlobDev);
+    if (pl->segOffsetsDev) cudaFree(pl->segOffsetsDev);
+    if (pl->inEvent) cudaEventDestroy(pl->inEvent);
+    delete pl;
+    return QTB_OK;
+}
+
+static int plan_upload_locked(qtb_ctx *ctx, qtb_plan *pl, const double *const *hostInputs) {
+    if (pl->nInputs > 0 && !hostInputs) return fail(QTB_ERR_INVALID, "null inputs");
+    ST(ensure_device(ctx));
+    if (pl->inEventValid) CU(cudaEventSynchronize(pl->inEvent));     // previous H2D finished reading the pinned blob
+    for (int i = 0; i < pl->nInputs; i++) {
+        if (!hostInputs[i]) return fail(QTB_ERR_EMPTY_INPUT, "null input tensor");
+        const size_t b = Pool::bytes(pl->inputRanks[i]);
+        if (pl->inputBlobOff[i] != (size_t)-1) memcpy(pl->inBlobHost + pl->inputBlobOff[i], hostInputs[i], b);
+        else CU(cudaMemcpyAsync(pl->inputDev[i], hostInputs[i], b, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.bytes_h2d += (long long)b;
+    }
+    if (pl->inBlobBytes) {
+        CU(cudaMemcpyAsync(pl->inBlobDev, pl->inBlobHost, pl->inBlobBytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaEventRecord(pl->inEvent, ctx->stream));
+        pl->inEventValid = true;
+    }
+    return QTB_OK;
+}
+
+static int plan_run_locked(qtb_ctx *ctx, qtb_plan *pl) {
+    ST(ensure_device(ctx));
+    ST(flush_locked(ctx));
+    const bool useGraph = plan_graphs_enabled() && !ctx->trace && pl->segs.size() >= 3;
+    if (useGraph && !pl->graphTried) {
+        pl->graphTried = true;
+        cudaGraph_t g = nullptr;
+        const long long launchesBefore = ctx->stats.launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int st = plan_enqueue(ctx, pl, ctx->stream);
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            ctx->stats.launches = launchesBefore;
+            if (st == QTB_OK && e == cudaSuccess && g) {
+                if (cudaGraphInstantiate(&pl->graph, g, 0) != cudaSuccess) { pl->graph = nullptr; cudaGetLastError(); }
+            } else cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+        } else cudaGetLastError();
+    }
+    if (useGraph && pl->graph) {
+        CU(cudaGraphLaunch(pl->graph, ctx->stream));
+        ctx->stats.launches += pl->launches;
+    } else {
+        ST(plan_enqueue(ctx, pl, ctx->stream));
+    }
+    ctx->stats.steps += pl->nSteps;
+    ctx->stats.micro_steps += pl->nMicroSteps;
+    ctx->stats.units += pl->units;
+    return QTB_OK;
+}
+
+static int plan_read_locked(qtb_ctx *ctx, qtb_plan *pl, double *hostOut) {
+    const size_t b = Pool::bytes(pl->outRank);
+    if (pl->outRank == 0) {
+        CU(cudaMemcpyAsync(ctx->scalarPinned, pl->outDev, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        hostOut[0] = ctx->scalarPinned[0]; hostOut[1] = ctx->scalarPinned[1];
+    } else {
+        CU(cudaMemcpyAsync(hostOut, pl->outDev, b, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->stats.bytes_d2h += (long long)b;
+    return QTB_OK;
+}
+
+int qtb_plan_upload_inputs(qtb_ctx *ctx, qtb_plan *pl, const double *const *hostInputs) {
+    if (!ctx || !pl) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return plan_upload_locked(ctx, pl, hostInputs);
+}
+int qtb_plan_run_device(qtb_ctx *ctx, qtb_plan *pl) {
+    if (!ctx || !pl) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return plan_run_locked(ctx, pl);
+}
+int qtb_plan_read_output(qtb_ctx *ctx, qtb_plan *pl, double *hostOut) {
+    if (!ctx || !pl || !hostOut) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return plan_read_locked(ctx, pl, hostOut);
+}
+int qtb_plan_run_host(qtb_ctx *ctx, qtb_plan *pl, const double *const *hostInputs, double *hostOut) {
+    if (!ctx || !pl || !hostOut) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(plan_upload_locked(ctx, pl, hostInputs));
+    ST(plan_run_locked(ctx, pl));
+    return plan_read_locked(ctx, pl, hostOut);
+}
+int qtb_plan_output_rank(qtb_plan *pl) { return pl ? pl->outRank : -1; }
+long long qtb_plan_units(qtb_plan *pl) { return pl ? pl->units : 0; }
+int qtb_plan_launches(qtb_plan *pl) { return pl ? pl->launches : 0; }
+
+}  // extern "C"

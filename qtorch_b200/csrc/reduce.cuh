@@ -1,0 +1,75 @@
+// qtorch_b200/csrc/reduce.cuh -- split-K kernel for steps with (almost) no free legs and a long sum,
+// e.g. the (14,14,k=14 -> 0) inner product that closes the QAOA-30 line-graph plan
+// (8.6 GB read once: HBM-bound).  Replaces the same loop of Network::ContractIndices
+// (/root/reference/src/Network.h:892-935) for rC <= 2.
+//
+//   C[c] = sum_s A[fA(c) + sA(s)] * B[fB(c) + sB(s)]
+// The summed index is cut into tiles of 256 (four legs chosen so that BOTH operands are read in
+// >= 256-byte runs); CTAs stride over tiles, every thread keeps NC complex accumulators, a block
+// reduction writes one partial per CTA and a second tiny kernel adds the partials in a fixed order
+// (deterministic, no atomics).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kernels.cuh"
+
+namespace qtb {
+
+struct ReduceParams {
+    const double2 *A;
+    const double2 *B;
+    double2 *partial;          // [gridDim.x][NC]
+    double2 *C;
+    uint32_t nTiles;           // 4^k / 256
+    uint8_t kbits;             // 2k
+    uint8_t shA[32], shB[32];  // summed bit j -> bit position inside A / B (bits 0..7 = tile)
+    uint32_t fA[16], fB[16];   // offsets of output element c inside A / B
+};
+
+__device__ __forceinline__ uint32_t scatter32(uint32_t v, const uint8_t *sh, int first, int count) {
+    uint32_t o = 0;
+    for (int j = 0; j < count; j++) o += ((v >> j) & 1u) << sh[first + j];
+    return o;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) k_reduce(const ReduceParams p) {
+    __shared__ double2 red[8][NC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tA = scatter32(tid, p.shA, 0, 8), tB = scatter32(tid, p.shB, 0, 8);
+    const int hi = p.kbits - 8;
+    double accR[NC], accI[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) { accR[c] = 0.0; accI[c] = 0.0; }
+    const double2 *__restrict__ A = p.A;
+    const double2 *__restrict__ B = p.B;
+#pragma unroll 2
+    for (uint32_t tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
+        const uint32_t oa = scatter32(tile, p.shA, 8, hi) + tA, ob = scatter32(tile, p.shB, 8, hi) + tB;
+#pragma unroll
+        for (int c = 0; c < NC; c++) cmac(accR[c], accI[c], A[(size_t)p.fA[c] + oa], B[(size_t)p.fB[c] + ob]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const double r = warp_sum(accR[c]), i = warp_sum(accI[c]);
+        if (lane == 0) red[warp][c] = make_double2(r, i);
+    }
+    __syncthreads();
+    if (tid < NC) {
+        double r = 0.0, i = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { r += red[w][tid].x; i += red[w][tid].y; }
+        p.partial[(size_t)blockIdx.x * NC + tid] = make_double2(r, i);
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(32 * NC) k_reduce_final(const double2 *__restrict__ partial, double2 *C, uint32_t nBlocks) {
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    double r = 0.0, i = 0.0;
+    for (uint32_t b = lane; b < nBlocks; b += 32) { const double2 v = partial[(size_t)b * NC + c]; r += v.x; i += v.y; }
+    r = warp_sum(r); i = warp_sum(i);
+    if (lane == 0) C[c] = make_double2(r, i);
+}
+
+}  // namespace qtb

@@ -1,0 +1,414 @@
+// qtorch_b200/host/Node.h -- tensor-network vertex with DEVICE-RESIDENT storage.
+//
+// Public surface = /root/reference/src/Node.h:108-166 (Node) and :197-898 (gate / measurement subclasses),
+// so planners, tests and user code compile unchanged.  What changed underneath:
+//   * the tensor (4^rank complex<double>, leg 0 fastest, Node.h:178-186) lives in HBM inside the engine's
+//     per-rank pool; the host vector the reference API hands out by reference (GetTensorVals / Index /
+//     Access, Node.h:119-121,151) is a LAZY MIRROR: it is materialised (zero-filled, or downloaded) only
+//     when host code actually looks, and any mutable host access marks the device copy stale so it is
+//     re-uploaded before the next contraction.  A rank-14 intermediate (4.29 GB) therefore never touches
+//     host memory, while gate constructors still write through Index({..}) exactly as before.
+//   * gate tensors are generated from the gates' unitaries,  S[in.., out..] = U[rho_o,rho_i]*conj(U[kappa_o,kappa_i])
+//     with wire digit d = 2*row + col of the density-matrix element (see tests/test_gates.py for the check
+//     against the reference's constant tables).
+#pragma once
+
+#define PI 3.14159265358979323846
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <numeric>
+#include <random>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "DeviceEngine.h"
+#include "Exceptions.h"
+#include "Wire.h"
+
+namespace qtorch {
+
+enum class GateType {
+    CNOT, SWAP, HADAMARD, RX, RY, RZ, X, Y, Z, PHASE, DEPOLARIZER, CRK, CZ, CPHASE,
+    INITSTATE, MEASURETRACE, INTERMEDIATESTATE, ARBITRARYONEQUBITUNITARY, ARBITRARYTWOQUBITUNITARY
+};
+
+class Node {
+public:
+    typedef std::complex<double> cplx;
+
+    int mRank;
+
+    explicit Node(int rank0) : mRank(rank0), mContracted(false), mSelectedInCostContractionAlgorithm(false) {}
+
+    // ---- host views (lazy mirror) ---------------------------------------------------------------
+    inline const cplx &Access(const std::vector<int> &digits) { return hostView().at(linearIndex(digits)); }
+    inline const cplx &Access(const long long &index) { return hostView().at(static_cast<size_t>(index)); }
+    inline cplx &Index(const std::vector<int> &digits) { return hostForWrite()[linearIndex(digits)]; }
+    inline cplx &Index(const long long &index) { return hostForWrite()[static_cast<size_t>(index)]; }
+    std::vector<cplx> &GetTensorVals() { return hostForWrite(); }
+
+    // Node::ClearNodeData (reference Node.h:137): drop host mirror and give the device buffer back to the pool
+    inline void ClearNodeData() {
+        std::vector<cplx>().swap(mVals);
+        mHost = HostState::Cleared;
+        releaseDevice();
+    }
+    // true until ClearNodeData(); replaces the reference's "GetTensorVals().size() == 0" probe (Network.h:938)
+    // without forcing a 4^rank host allocation
+    bool HasData() const { return mHost != HostState::Cleared; }
+    size_t NumElements() const { return static_cast<size_t>(1) << (2 * mRank); }
+
+    // ---- device side ------------------------------------------------------------------------------
+    // Handle whose contents equal the node's logical tensor (uploads the host mirror if it is newer).
+    qtb_tensor DeviceTensor() {
+        if (mHost == HostState::Cleared) throw InvalidFunctionInput();
+        qtb_ctx *ctx = device::Engine::Get().ctx();
+        if (!mDev) device::check(qtb_tensor_alloc(ctx, mRank, &mDev));
+        if (!mDevValid) {
+            const std::vector<cplx> &v = hostView();
+            device::check(qtb_tensor_upload(ctx, mDev, reinterpret_cast<const double *>(v.data())));
+            mDevValid = true;
+        }
+        return mDev;
+    }
+    // Fresh output buffer for a contraction result: the device copy becomes the truth.
+    qtb_tensor DeviceOutput() {
+        qtb_ctx *ctx = device::Engine::Get().ctx();
+        if (!mDev) device::check(qtb_tensor_alloc(ctx, mRank, &mDev));
+        mDevValid = true;
+        mHost = HostState::Stale;
+        std::vector<cplx>().swap(mVals);
+        return mDev;
+    }
+    bool OnDevice() const { return mDev != nullptr && mDevValid; }
+
+    // ---- circuit bookkeeping (unchanged semantics) ---------------------------------------------------
+    inline const std::vector<int> &GetWireNumber() const { return mWireNumbers; }
+    inline void AddWireNumber(const int q) { mWireNumbers.push_back(q); }
+    inline void SetWireNumber(const int index, const int q) { mWireNumbers[index] = q; }
+    inline const GateType GetTypeOfNode() const { return mType; }
+    inline void SetTypeOfNode(GateType t) { mType = t; }
+    inline void SetTypeOfNodeString(const std::string &s) { mStringType = s; }
+    inline const std::string &GetTypeOfNodeString() const { return mStringType; }
+
+    int mID{0};
+    int mIndexOfPreviousNode{0};
+    bool mContracted;
+    std::pair<int, int> mCreatedFrom{0, 0};
+    bool mSelectedInCostContractionAlgorithm;
+
+    std::vector<std::shared_ptr<Wire>> &GetWires() {
+        if (static_cast<int>(mWires.size()) > mRank)
+            std::cout << "Node rank is:" << mRank << " and num wires is:" << mWires.size() << std::endl;
+        return mWires;
+    }
+
+    virtual ~Node() { releaseDevice(); }
+    Node(const Node &o) { copyFrom(o); }
+    Node &operator=(const Node &o) {
+        if (this != &o) { releaseDevice(); copyFrom(o); }
+        return *this;
+    }
+    Node(Node &&o) { copyFrom(o); }
+    Node &operator=(Node &&o) {
+        if (this != &o) { releaseDevice(); copyFrom(o); }
+        return *this;
+    }
+
+private:
+    enum class HostState { Unset /* logically all-zero, not allocated */, Valid, Stale /* device is newer */, Cleared };
+
+    static size_t linearIndex(const std::vector<int> &digits) {
+        size_t idx = 0;
+        int shift = 0;
+        for (int d : digits) { idx += static_cast<size_t>(d) << shift; shift += 2; }
+        return idx;
+    }
+    std::vector<cplx> &hostView() {
+        if (mHost == HostState::Unset) {
+            mVals.assign(NumElements(), cplx(0.0, 0.0));            // reference Node.h:112-113 zero fill
+            mHost = HostState::Valid;
+        } else if (mHost == HostState::Stale) {
+            mVals.resize(NumElements());
+            if (device::Engine::PlanOnly() || !mDev) {
+                std::fill(mVals.begin(), mVals.end(), cplx(std::numeric_limits<double>::quiet_NaN(), 0.0));
+            } else {
+                device::check(qtb_tensor_download(device::Engine::Get().ctx(), mDev, reinterpret_cast<double *>(mVals.data())));
+            }
+            mHost = HostState::Valid;
+        }
+        return mVals;
+    }
+    std::vector<cplx> &hostForWrite() {
+        std::vector<cplx> &v = hostView();
+        if (mHost != HostState::Cleared) mDevValid = false;       // caller may modify: device copy is stale now
+        return v;
+    }
+    void releaseDevice() {
+        if (mDev) {
+            if (device::Engine::Get().alive()) qtb_tensor_free(device::Engine::Get().ctx(), mDev);
+            mDev = nullptr;
+        }
+        mDevValid = false;
+    }
+    void copyFrom(const Node &o) {
+        Node &src = const_cast<Node &>(o);
+        mRank = o.mRank; mID = o.mID; mIndexOfPreviousNode = o.mIndexOfPreviousNode; mContracted = o.mContracted;
+        mCreatedFrom = o.mCreatedFrom; mSelectedInCostContractionAlgorithm = o.mSelectedInCostContractionAlgorithm;
+        mWires = o.mWires; mWireNumbers = o.mWireNumbers; mType = o.mType; mStringType = o.mStringType;
+        if (o.mHost == HostState::Cleared) { mVals.clear(); mHost = HostState::Cleared; }
+        else if (o.mHost == HostState::Unset) { mVals.clear(); mHost = HostState::Unset; }
+        else { mVals = src.hostView(); mHost = HostState::Valid; }
+        mDev = nullptr; mDevValid = false;
+    }
+
+    std::vector<cplx> mVals;
+    HostState mHost{HostState::Unset};
+    qtb_tensor mDev{nullptr};
+    bool mDevValid{false};
+    std::vector<std::shared_ptr<Wire>> mWires;
+    std::vector<int> mWireNumbers;
+
+protected:
+    GateType mType{GateType::INTERMEDIATESTATE};
+    std::string mStringType{"INTERMEDIATESTATE"};
+
+    // ---- superoperator builders -----------------------------------------------------------------------
+    // wire digit d <-> density-matrix element |row><col| with d = 2*row + col
+    static int rowOf(int d) { return d >> 1; }
+    static int colOf(int d) { return d & 1; }
+
+    // rank-2 tensor S[in, out] of a 2x2 operator U (row-major), scaled by `scale`
+    void fillFromUnitary1(const cplx U[4], double scale = 1.0) {
+        for (int in = 0; in < 4; ++in)
+            for (int out = 0; out < 4; ++out)
+                Index({in, out}) = U[2 * rowOf(out) + rowOf(in)] * std::conj(U[2 * colOf(out) + colOf(in)]) * scale;
+    }
+    // rank-4 tensor S[in1, in2, out1, out2] of a 4x4 operator U (row-major, basis |q1 q2>)
+    void fillFromUnitary2(const cplx U[16]) {
+        for (int i1 = 0; i1 < 4; ++i1)
+            for (int i2 = 0; i2 < 4; ++i2)
+                for (int o1 = 0; o1 < 4; ++o1)
+                    for (int o2 = 0; o2 < 4; ++o2) {
+                        const int rhoIn = 2 * rowOf(i1) + rowOf(i2), kapIn = 2 * colOf(i1) + colOf(i2);
+                        const int rhoOut = 2 * rowOf(o1) + rowOf(o2), kapOut = 2 * colOf(o1) + colOf(o2);
+                        Index({i1, i2, o1, o2}) = U[4 * rhoOut + rhoIn] * std::conj(U[4 * kapOut + kapIn]);
+                    }
+    }
+    // diag(1, phase) on one qubit: only the coherences pick up a phase, populations stay exactly 1
+    void fillPhaseGate1(const cplx &phase) {
+        Index({0, 0}) = 1.0;
+        Index({1, 1}) = std::conj(phase);
+        Index({2, 2}) = phase;
+        Index({3, 3}) = 1.0;
+    }
+    // diag(1, 1, 1, phase) on two qubits
+    void fillPhaseGate2(const cplx &phase) {
+        for (int d1 = 0; d1 < 4; ++d1)
+            for (int d2 = 0; d2 < 4; ++d2) {
+                const bool rowHit = (rowOf(d1) == 1 && rowOf(d2) == 1), colHit = (colOf(d1) == 1 && colOf(d2) == 1);
+                cplx v(1.0, 0.0);
+                if (rowHit && !colHit) v = phase;
+                else if (colHit && !rowHit) v = std::conj(phase);
+                Index({d1, d2, d1, d2}) = v;
+            }
+    }
+};
+
+// ---- one-qubit gates ---------------------------------------------------------------------------------
+class HNode : public Node {
+public:
+    HNode() : Node(2) {
+        const cplx U[4] = {1.0, 1.0, 1.0, -1.0};
+        fillFromUnitary1(U, 0.5);                      // (1/sqrt2)^2 applied once, exactly
+        mType = GateType::HADAMARD; mStringType = "H";
+    }
+};
+class XNode : public Node {
+public:
+    XNode() : Node(2) {
+        const cplx U[4] = {0.0, 1.0, 1.0, 0.0};
+        fillFromUnitary1(U);
+        mType = GateType::X; mStringType = "X";
+    }
+};
+class YNode : public Node {
+public:
+    YNode() : Node(2) {
+        const cplx U[4] = {0.0, cplx(0, -1), cplx(0, 1), 0.0};
+        fillFromUnitary1(U);
+        mType = GateType::Y; mStringType = "Y";
+    }
+};
+class ZNode : public Node {
+public:
+    ZNode() : Node(2) {
+        fillPhaseGate1(cplx(-1.0, 0.0));
+        mType = GateType::Z; mStringType = "Z";
+    }
+};
+// Rx(t) = exp(-i t X / 2)
+class RxNode : public Node {
+public:
+    RxNode(const double t) : Node(2) {
+        const double c = std::cos(t / 2.0), s = std::sin(t / 2.0);
+        const cplx U[4] = {c, cplx(0, -s), cplx(0, -s), c};
+        fillFromUnitary1(U);
+        mType = GateType::RX; mStringType = "Rx";
+    }
+};
+// Ry(t) = exp(-i t Y / 2)
+class RyNode : public Node {
+public:
+    RyNode(const double t) : Node(2) {
+        const double c = std::cos(t / 2.0), s = std::sin(t / 2.0);
+        const cplx U[4] = {c, -s, s, c};
+        fillFromUnitary1(U);
+        mType = GateType::RY; mStringType = "Ry";
+    }
+};
+// Rz(t) = diag(1, e^{it}) up to a global phase
+class RzNode : public Node {
+public:
+    RzNode(const double t) : Node(2) {
+        fillPhaseGate1(cplx(std::cos(t), std::sin(t)));
+        mType = GateType::RZ; mStringType = "Rz";
+    }
+};
+class PhaseNode : public Node {
+public:
+    PhaseNode(const double t) : Node(2) {
+        fillPhaseGate1(cplx(std::cos(t), std::sin(t)));
+        mType = GateType::PHASE; mStringType = "Phase";
+    }
+};
+// depolarising channel with a random strength (no parser keyword reaches it; kept for API parity, Node.h:500-513)
+class DepolarizingChannelNode : public Node {
+public:
+    DepolarizingChannelNode(std::mt19937 &gen, std::uniform_real_distribution<float> &randDist) : Node(2) {
+        const float p = randDist(gen);
+        const double keep = 1.0 - (2.0 * p / 3.0), coh = 1.0 - (4.0 * p / 3.0), mix = 2.0 * p / 3.0;
+        Index({0, 0}) = keep; Index({3, 3}) = keep;
+        Index({1, 1}) = coh;  Index({2, 2}) = coh;
+        Index({1, 2}) = mix;  Index({2, 1}) = mix;
+        mType = GateType::DEPOLARIZER; mStringType = "Depolarizer";
+    }
+};
+
+// ---- rank-1 nodes: initial state, trace, measurements -------------------------------------------------------
+class ZeroStateNode : public Node {
+public:
+    ZeroStateNode() : Node(1) { Index({0}) = 1; mType = GateType::INITSTATE; mStringType = "|0><0|"; }
+};
+class TraceNode : public Node {
+public:
+    TraceNode() : Node(1) { Index({0}) = 1.0; Index({3}) = 1.0; mType = GateType::MEASURETRACE; mStringType = "Trace"; }
+};
+class XMeasure : public Node {
+public:
+    XMeasure() : Node(1) { Index({1}) = 1.0; Index({2}) = 1.0; mType = GateType::MEASURETRACE; mStringType = "X measure"; }
+};
+class YMeasure : public Node {
+public:
+    YMeasure() : Node(1) {
+        Index({1}) = cplx(0, 1.0); Index({2}) = cplx(0, -1.0);
+        mType = GateType::MEASURETRACE; mStringType = "Y measure";
+    }
+};
+class ZMeasure : public Node {
+public:
+    ZMeasure() : Node(1) { Index({0}) = 1.0; Index({3}) = -1.0; mType = GateType::MEASURETRACE; mStringType = "Z measure"; }
+};
+class ProjectOne : public Node {
+public:
+    ProjectOne() : Node(1) { Index({3}) = 1; mType = GateType::MEASURETRACE; mStringType = "|1><1| measure"; }
+};
+class ProjectZero : public Node {
+public:
+    ProjectZero() : Node(1) { Index({0}) = 1; mType = GateType::MEASURETRACE; mStringType = "|0><0| measure"; }
+};
+
+// ---- two-qubit gates (wire order [in_q1, in_q2, out_q1, out_q2], reference Network.h:522-531) ---------------
+class CNOTNode : public Node {
+public:
+    CNOTNode() : Node(4) {
+        cplx U[16] = {};
+        U[4 * 0 + 0] = 1; U[4 * 1 + 1] = 1; U[4 * 3 + 2] = 1; U[4 * 2 + 3] = 1;
+        fillFromUnitary2(U);
+        mType = GateType::CNOT; mStringType = "CNOT";
+    }
+};
+class SwapNode : public Node {
+public:
+    SwapNode() : Node(4) {
+        cplx U[16] = {};
+        U[4 * 0 + 0] = 1; U[4 * 2 + 1] = 1; U[4 * 1 + 2] = 1; U[4 * 3 + 3] = 1;
+        fillFromUnitary2(U);
+        mType = GateType::SWAP; mStringType = "SWAP";
+    }
+};
+// controlled-R_k; NOTE the reference passes the CONTROL QUBIT INDEX as k (Network.h:571, Node.h:426-442)
+class CRkNode : public Node {
+public:
+    CRkNode(int controlBit) : Node(4) {
+        fillPhaseGate2(std::exp(2.0 * PI * cplx(0, 1) / std::pow(2, controlBit + 1.0)));
+        mType = GateType::CRK; mStringType = "CRk";
+    }
+};
+class CZNode : public Node {
+public:
+    CZNode() : Node(4) {
+        fillPhaseGate2(cplx(-1.0, 0.0));
+        mType = GateType::CZ; mStringType = "CZ";
+    }
+};
+class CPhaseNode : public Node {
+public:
+    CPhaseNode(double t) : Node(4) {
+        fillPhaseGate2(cplx(std::cos(t), std::sin(t)));
+        mStringType = "CPhase"; mType = GateType::CPHASE;
+    }
+};
+
+// ---- user-defined gates: matrix file with 4 / 16 entries "(re,im)", row-major (reference Node.h:557-896) ------
+namespace detail {
+inline std::vector<std::complex<double>> readMatrixFile(const std::string &filename, int count) {
+    std::ifstream input(filename);
+    if (!input.is_open()) {
+        std::cout << "Failed To Open Arbitrary Matrix File" << std::endl;
+        throw InvalidFile();
+    }
+    std::vector<std::complex<double>> nums(count);
+    for (int i = 0; i < count; ++i) {
+        if (input.eof()) throw InvalidFileFormat();
+        input >> nums[i];
+    }
+    return nums;
+}
+}  // namespace detail
+
+class ArbitraryOneQubitNode : public Node {
+public:
+    ArbitraryOneQubitNode(const std::string &inputFile, const std::string &nodeName) : Node(2) {
+        mType = GateType::ARBITRARYONEQUBITUNITARY; mStringType = nodeName;
+        const std::vector<cplx> m = detail::readMatrixFile(inputFile, 4);
+        fillFromUnitary1(m.data());
+    }
+};
+class ArbitraryTwoQubitNode : public Node {
+public:
+    ArbitraryTwoQubitNode(const std::string &inputFile, const std::string &nodeName) : Node(4) {
+        mType = GateType::ARBITRARYTWOQUBITUNITARY; mStringType = nodeName;
+        const std::vector<cplx> m = detail::readMatrixFile(inputFile, 16);
+        fillFromUnitary2(m.data());
+    }
+};
+
+}  // namespace qtorch
