@@ -108,6 +108,11 @@ int qtb_plan_upload_inputs(qtb_ctx *ctx, qtb_plan *plan, const double *const *ho
 int qtb_plan_run_device(qtb_ctx *ctx, qtb_plan *plan);
 int qtb_plan_read_output(qtb_ctx *ctx, qtb_plan *plan, double *host_out);
 int qtb_plan_output_rank(qtb_plan *plan);
+/* Several input sets resident in HBM at once (e.g. the per-edge measurement caps of all <ZiZj> terms):
+ * stage set `slot` once, then run the plan on it with a device-to-device copy of the small-input blob.
+ * Only for plans whose inputs all have rank <= 5 (gate / state / measurement tensors).                  */
+int qtb_plan_stage_inputs(qtb_ctx *ctx, qtb_plan *plan, int slot, const double *const *host_inputs);
+int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *plan, int slot);
 /* sum_steps 4^(rC+k): the reference's getNumFloatOps() contribution of this plan (Network.h:884-885). */
 long long qtb_plan_units(qtb_plan *plan);
 /* Number of kernel launches one qtb_plan_run_device enqueues. */
@@ -138,6 +143,10 @@ typedef struct qtb_step_trace {
     int32_t rank_a, rank_b, k, kernel;   /* kernel: 0 micro-group, 1 generic, 2 tiled DMMA, 3 streaming */
     float ms;
 } qtb_step_trace;
+/* CUDA-event stopwatch on the ctx stream (bench.py times the hot path with it): start flushes deferred work
+ * and records an event; stop flushes, records, waits and returns the elapsed milliseconds.             */
+int qtb_ctx_timer_start(qtb_ctx *ctx);
+int qtb_ctx_timer_stop(qtb_ctx *ctx, float *ms);
 int qtb_ctx_trace_enable(qtb_ctx *ctx, int on);
 int qtb_ctx_trace_read(qtb_ctx *ctx, qtb_step_trace *out, int max_entries, int *n_entries);
 

@@ -25,9 +25,9 @@ ABI_SYMBOLS = [
     "qtb_tensor_alloc", "qtb_tensor_free", "qtb_tensor_rank", "qtb_tensor_device_ptr",
     "qtb_tensor_upload", "qtb_tensor_download", "qtb_read_scalar", "qtb_contract",
     "qtb_plan_create", "qtb_plan_destroy", "qtb_plan_run_host", "qtb_plan_upload_inputs",
-    "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
+    "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_stage_inputs", "qtb_plan_run_device_slot", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
     "qtb_comm_unique_id", "qtb_comm_init", "qtb_comm_destroy", "qtb_allreduce_sum",
-    "qtb_ctx_stats", "qtb_ctx_reset_stats", "qtb_ctx_trace_enable", "qtb_ctx_trace_read",
+    "qtb_ctx_stats", "qtb_ctx_reset_stats", "qtb_ctx_timer_start", "qtb_ctx_timer_stop", "qtb_ctx_trace_enable", "qtb_ctx_trace_read",
 ]
 
 
@@ -93,6 +93,10 @@ def load_library():
     L.qtb_plan_upload_inputs.argtypes = [vp, vp, ctypes.POINTER(vp)]
     L.qtb_plan_run_device.argtypes = [vp, vp]
     L.qtb_plan_read_output.argtypes = [vp, vp, vp]
+    L.qtb_plan_stage_inputs.argtypes = [vp, vp, ci, ctypes.POINTER(vp)]
+    L.qtb_plan_run_device_slot.argtypes = [vp, vp, ci]
+    L.qtb_ctx_timer_start.argtypes = [vp]
+    L.qtb_ctx_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.qtb_plan_output_rank.argtypes = [vp]
     L.qtb_plan_units.restype = ctypes.c_longlong
     L.qtb_plan_units.argtypes = [vp]
@@ -199,6 +203,12 @@ class Plan:
     def run_device(self):
         _check(self.engine.lib.qtb_plan_run_device(self.engine.ctx, self.handle))
 
+    def stage_inputs(self, slot, host_inputs):
+        _check(self.engine.lib.qtb_plan_stage_inputs(self.engine.ctx, self.handle, slot, self._ptrs(host_inputs)))
+
+    def run_device_slot(self, slot):
+        _check(self.engine.lib.qtb_plan_run_device_slot(self.engine.ctx, self.handle, slot))
+
     def read_output(self):
         out = np.empty(4 ** self.output_rank, dtype=np.complex128)
         _check(self.engine.lib.qtb_plan_read_output(self.engine.ctx, self.handle, out.ctypes.data))
@@ -213,8 +223,12 @@ class Plan:
 class Engine:
     """One qtb_ctx: device, stream, pooled tensor storage, deferred micro-steps."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, ctx=None):
         self.lib = load_library()
+        if ctx is not None:                       # wrap an existing qtb_ctx (e.g. the host mirror's singleton)
+            self.ctx, self.device, self._borrowed = ctypes.c_void_p(ctx), device, True
+            return
+        self._borrowed = False
         if device is None:
             device = int(os.environ.get("QTORCH_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         h = ctypes.c_void_p()
@@ -255,6 +269,14 @@ class Engine:
     def reset_stats(self):
         _check(self.lib.qtb_ctx_reset_stats(self.ctx))
 
+    def timer_start(self):
+        _check(self.lib.qtb_ctx_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        _check(self.lib.qtb_ctx_timer_stop(self.ctx, ctypes.byref(ms)))
+        return ms.value
+
     def trace(self, on=True):
         _check(self.lib.qtb_ctx_trace_enable(self.ctx, 1 if on else 0))
 
@@ -279,9 +301,9 @@ class Engine:
         return v
 
     def close(self):
-        if self.ctx:
+        if self.ctx and not self._borrowed:
             self.lib.qtb_ctx_destroy(self.ctx)
-            self.ctx = None
+        self.ctx = None
 
 
 # ---- host-mirror drivers (C++ binaries) -----------------------------------------------------------------------

@@ -1,0 +1,126 @@
+// qtorch_b200/apps/host_capi.cpp -> qtorch_b200/libqtorch_host.so
+// In-process C entry points over the C++ host mirror (Network / LineGraph / ContractionTools), so that
+// bench.py and the tests can make "the call a user makes" -- build the Network from .qasm + measurement
+// files, ReduceCircuit, contract along a frozen QuickBB ordering or a recorded plan, read the value --
+// without paying process start-up and CUDA initialisation per call.  Same flow as qtorch's main.cpp
+// (/root/reference/src/main.cpp:74-198).
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../host/qtorch.hpp"
+
+static thread_local std::string g_err;
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+extern "C" {
+
+const char *qth_last_error(void) { return g_err.c_str(); }
+
+// the process-wide engine context of the host mirror (for qtb_ctx_stats / timers / trace from the caller)
+void *qth_engine_ctx(void) {
+    try { return device::Engine::Get().ctx(); } catch (std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
+// Network(qasm, measure) -> [ReduceCircuit] -> LineGraph(net).LGContract() on the frozen ordering -> GetFinalValue().
+// seconds_after_parse mirrors the reference's own stopwatch (started after the circuit is read, main.cpp:108-109).
+int qth_contract_linegraph(const char *qasm, const char *measure, const char *qbbOut, int reduce, double value[2],
+                           long long *flops, int *nodes, double *secondsAfterParse) {
+    try {
+        auto net = std::make_shared<Network>(qasm, measure);
+        const double t0 = now_s();
+        if (reduce) net->ReduceCircuit();
+        LineGraph lg(net);
+        lg.SetQBBOutFiles("/dev/null", qbbOut, "/dev/null");
+        const bool ok = lg.LGContract();
+        const std::complex<double> v = net->GetFinalValue();
+        if (secondsAfterParse) *secondsAfterParse = now_s() - t0;
+        value[0] = v.real(); value[1] = v.imag();
+        if (flops) *flops = net->getNumFloatOps();
+        if (nodes) *nodes = static_cast<int>(net->GetAllNodes().size());
+        return ok ? 0 : 2;
+    } catch (std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// ContractionTools(qasm, measure).ContractGivenSequence(pairs): replay of a recorded plan (mCreatedFrom pairs).
+int qth_contract_sequence(const char *qasm, const char *measure, const int *pairs, int nPairs, double value[2],
+                          long long *flops, int *nodes, double *secondsAfterParse) {
+    try {
+        std::vector<std::pair<int, int>> seq(nPairs);
+        for (int i = 0; i < nPairs; i++) seq[i] = {pairs[2 * i], pairs[2 * i + 1]};
+        auto net = std::make_shared<Network>(qasm, measure);
+        ContractionTools tools(net);
+        const double t0 = now_s();
+        tools.ContractGivenSequence(seq);
+        const std::complex<double> v = tools.GetFinalVal();
+        if (secondsAfterParse) *secondsAfterParse = now_s() - t0;
+        value[0] = v.real(); value[1] = v.imag();
+        if (flops) *flops = net->getNumFloatOps();
+        if (nodes) *nodes = static_cast<int>(net->GetAllNodes().size());
+        return 0;
+    } catch (std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// Plan export without touching the device (host bookkeeping only): runs the same flow in plan-only mode and
+// returns the step list in qtb_plan_step layout plus every original node's tensor (the plan's inputs).
+// Buffers are owned by the library until the next call on this thread.
+struct QthPlan {
+    int nInputs, nSteps;
+    const int *inputRanks;
+    const double *inputData;        // concatenated (re,im) of all inputs in id order
+    const long long *inputOffsets;  // element offset (in complex numbers) of input i inside inputData
+    const qtb_plan_step *steps;
+    long long flops;
+};
+static thread_local std::vector<int> t_ranks;
+static thread_local std::vector<double> t_data;
+static thread_local std::vector<long long> t_offs;
+static thread_local std::vector<qtb_plan_step> t_steps;
+
+int qth_export_plan_linegraph(const char *qasm, const char *measure, const char *qbbOut, int reduce, QthPlan *out) {
+    const bool before = device::Engine::PlanOnly();
+    device::Engine::SetPlanOnly(true);
+    int rc = 0;
+    try {
+        auto net = std::make_shared<Network>(qasm, measure);
+        const int n = static_cast<int>(net->GetAllNodes().size());
+        t_ranks.clear(); t_data.clear(); t_offs.clear(); t_steps.clear();
+        for (int i = 0; i < n; i++) {
+            auto &node = net->GetAllNodes()[i];
+            t_ranks.push_back(node->mRank);
+            t_offs.push_back(static_cast<long long>(t_data.size() / 2));
+            for (size_t e = 0; e < node->NumElements(); e++) {
+                const std::complex<double> &v = node->Access(static_cast<long long>(e));
+                t_data.push_back(v.real()); t_data.push_back(v.imag());
+            }
+        }
+        if (reduce) net->ReduceCircuit();
+        LineGraph lg(net);
+        lg.SetQBBOutFiles("/dev/null", qbbOut, "/dev/null");
+        if (!lg.LGContract()) rc = 2;
+        for (const auto &r : net->GetPlan()) {
+            qtb_plan_step s;
+            memset(&s, 0, sizeof(s));
+            s.a = r.a; s.b = r.b; s.k = static_cast<int>(r.posA.size());
+            for (int j = 0; j < s.k; j++) { s.pos_a[j] = static_cast<int8_t>(r.posA[j]); s.pos_b[j] = static_cast<int8_t>(r.posB[j]); }
+            t_steps.push_back(s);
+        }
+        out->nInputs = n; out->nSteps = static_cast<int>(t_steps.size());
+        out->inputRanks = t_ranks.data(); out->inputData = t_data.data(); out->inputOffsets = t_offs.data();
+        out->steps = t_steps.data(); out->flops = net->getNumFloatOps();
+    } catch (std::exception &e) {
+        g_err = e.what();
+        rc = 1;
+    }
+    device::Engine::SetPlanOnly(before);
+    return rc;
+}
+
+}  // extern "C"

@@ -53,6 +53,12 @@ def build_host(force=False):
                    "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
             subprocess.run(cmd, check=True)
         out.append(target)
+    target = os.path.join(HERE, "libqtorch_host.so")
+    source = os.path.join(HERE, "apps", "host_capi.cpp")
+    if force or _newer(target, hdrs + [source]):
+        subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-o", target, source, "-L" + HERE, "-lqtorch_b200",
+                        "-Wl,-rpath,$ORIGIN", "-lpthread"], check=True)
+    out.append(target)
     return out
 
 

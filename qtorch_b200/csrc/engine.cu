@@ -308,6 +308,7 @@ struct qtb_ctx_s {
     qtb_stats stats{};
     bool trace = false;
     std::vector<TraceRec> traceRecs;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     // NCCL
     void *comm = nullptr; int nRanks = 1, rank = 0;
     double *commBuf = nullptr; size_t commBufElems = 0;
@@ -701,6 +702,26 @@ int qtb_ctx_reset_stats(qtb_ctx *ctx) {
     if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->stats = qtb_stats{};
+    return QTB_OK;
+}
+int qtb_ctx_timer_start(qtb_ctx *ctx) {
+    if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    ST(flush_locked(ctx));
+    if (!ctx->timer0) { CU(cudaEventCreate(&ctx->timer0)); CU(cudaEventCreate(&ctx->timer1)); }
+    CU(cudaEventRecord(ctx->timer0, ctx->stream));
+    return QTB_OK;
+}
+int qtb_ctx_timer_stop(qtb_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return fail(QTB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->timer0) return fail(QTB_ERR_INVALID, "timer not started");
+    ST(ensure_device(ctx));
+    ST(flush_locked(ctx));
+    CU(cudaEventRecord(ctx->timer1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->timer1));
+    CU(cudaEventElapsedTime(ms, ctx->timer0, ctx->timer1));
     return QTB_OK;
 }
 int qtb_ctx_trace_enable(qtb_ctx *ctx, int on) {

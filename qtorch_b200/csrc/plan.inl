@@ -28,6 +28,7 @@ struct qtb_plan_s {
     double2 *outDev = nullptr; int outRank = 0;
     long long units = 0; int nSteps = 0, nMicroSteps = 0; int launches = 0;
     cudaGraphExec_t graph = nullptr; bool graphTried = false;
+    std::vector<uint8_t *> slotDev;          // extra resident copies of the small-input blob
 };
 
 static bool plan_graphs_enabled() {
@@ -192,6 +193,7 @@ int qtb_plan_destroy(qtb_ctx *ctx, qtb_plan *pl) {
     if (pl->microBlobDev) cudaFree(pl->microBlobDev);
     if (pl->segOffsetsDev) cudaFree(pl->segOffsetsDev);
     if (pl->inEvent) cudaEventDestroy(pl->inEvent);
+    for (uint8_t *p : pl->slotDev) if (p) cudaFree(p);
     delete pl;
     return QTB_OK;
 }
@@ -280,6 +282,32 @@ int qtb_plan_run_host(qtb_ctx *ctx, qtb_plan *pl, const double *const *hostInput
     ST(plan_upload_locked(ctx, pl, hostInputs));
     ST(plan_run_locked(ctx, pl));
     return plan_read_locked(ctx, pl, hostOut);
+}
+int qtb_plan_stage_inputs(qtb_ctx *ctx, qtb_plan *pl, int slot, const double *const *hostInputs) {
+    if (!ctx || !pl || slot < 0 || slot > 4096 || !hostInputs) return fail(QTB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    for (int i = 0; i < pl->nInputs; i++)
+        if (pl->inputBlobOff[i] == (size_t)-1) return fail(QTB_ERR_UNSUPPORTED, "input slots need every input to have rank <= 5");
+    if ((size_t)slot >= pl->slotDev.size()) pl->slotDev.resize(slot + 1, nullptr);
+    if (!pl->slotDev[slot]) CU(cudaMalloc((void **)&pl->slotDev[slot], std::max<size_t>(pl->inBlobBytes, 256)));
+    if (pl->inEventValid) CU(cudaEventSynchronize(pl->inEvent));
+    for (int i = 0; i < pl->nInputs; i++) {
+        if (!hostInputs[i]) return fail(QTB_ERR_EMPTY_INPUT, "null input tensor");
+        memcpy(pl->inBlobHost + pl->inputBlobOff[i], hostInputs[i], Pool::bytes(pl->inputRanks[i]));
+        ctx->stats.bytes_h2d += (long long)Pool::bytes(pl->inputRanks[i]);
+    }
+    CU(cudaMemcpyAsync(pl->slotDev[slot], pl->inBlobHost, pl->inBlobBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(pl->inEvent, ctx->stream));
+    pl->inEventValid = true;
+    return QTB_OK;
+}
+int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *pl, int slot) {
+    if (!ctx || !pl || slot < 0 || (size_t)slot >= pl->slotDev.size() || !pl->slotDev[slot]) return fail(QTB_ERR_INVALID, "unknown input slot");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    CU(cudaMemcpyAsync(pl->inBlobDev, pl->slotDev[slot], pl->inBlobBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return plan_run_locked(ctx, pl);
 }
 int qtb_plan_output_rank(qtb_plan *pl) { return pl ? pl->outRank : -1; }
 long long qtb_plan_units(qtb_plan *pl) { return pl ? pl->units : 0; }

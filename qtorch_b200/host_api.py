@@ -1,0 +1,99 @@
+"""ctypes face of libqtorch_host.so: the C++ host mirror (Network / LineGraph / ContractionTools) called in-process.
+
+``contract_linegraph`` is "the call a user makes" -- the flow of qtorch's main.cpp (/root/reference/src/main.cpp:74-198):
+Network(qasm, measure) -> ReduceCircuit -> LineGraph(net).LGContract() on a frozen QuickBB ordering -> GetFinalValue().
+``export_plan_linegraph`` runs the same host bookkeeping without the device and returns the plan + input tensors in the
+layout qtb_plan_create expects.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import PlanStep, load_library, DeviceUnavailable, Engine, QTB_MAX_RANK
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libqtorch_host.so")
+_hlib = None
+
+
+class _QthPlan(ctypes.Structure):
+    _fields_ = [("nInputs", ctypes.c_int), ("nSteps", ctypes.c_int), ("inputRanks", ctypes.POINTER(ctypes.c_int)),
+                ("inputData", ctypes.POINTER(ctypes.c_double)), ("inputOffsets", ctypes.POINTER(ctypes.c_longlong)),
+                ("steps", ctypes.POINTER(PlanStep)), ("flops", ctypes.c_longlong)]
+
+
+def host_library():
+    global _hlib
+    if _hlib is None:
+        load_library()                                     # libqtorch_b200.so first (rpath covers it too)
+        if not os.path.exists(HOST_LIB_PATH):
+            raise DeviceUnavailable("libqtorch_host.so is not built (run `python -m qtorch_b200.build`)")
+        os.environ.setdefault("QTORCH_QUIET", "1")
+        H = ctypes.CDLL(HOST_LIB_PATH)
+        H.qth_last_error.restype = ctypes.c_char_p
+        H.qth_engine_ctx.restype = ctypes.c_void_p
+        cd, cll, ci = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)
+        H.qth_contract_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, cd, cll, ci, cd]
+        H.qth_contract_sequence.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ctypes.c_int, cd, cll, ci, cd]
+        H.qth_export_plan_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_QthPlan)]
+        _hlib = H
+    return _hlib
+
+
+def _raise(H, rc):
+    msg = H.qth_last_error().decode()
+    if "device engine unavailable" in msg:
+        raise DeviceUnavailable(msg)
+    raise RuntimeError("host mirror failed (rc=%d): %s" % (rc, msg))
+
+
+def engine():
+    """The host mirror's process-wide engine context, wrapped for stats / timers / trace."""
+    H = host_library()
+    ctx = H.qth_engine_ctx()
+    if not ctx:
+        _raise(H, 1)
+    return Engine(ctx=ctx)
+
+
+def contract_linegraph(qasm, measure, ordering, reduce=True):
+    H = host_library()
+    v = (ctypes.c_double * 2)()
+    flops, nodes, secs = ctypes.c_longlong(), ctypes.c_int(), ctypes.c_double()
+    rc = H.qth_contract_linegraph(qasm.encode(), measure.encode(), ordering.encode(), 1 if reduce else 0, v,
+                                  ctypes.byref(flops), ctypes.byref(nodes), ctypes.byref(secs))
+    if rc != 0:
+        _raise(H, rc)
+    return complex(v[0], v[1]), flops.value, nodes.value, secs.value
+
+
+def contract_sequence(qasm, measure, pairs):
+    H = host_library()
+    flat = (ctypes.c_int * (2 * len(pairs)))(*[x for p in pairs for x in p])
+    v = (ctypes.c_double * 2)()
+    flops, nodes, secs = ctypes.c_longlong(), ctypes.c_int(), ctypes.c_double()
+    rc = H.qth_contract_sequence(qasm.encode(), measure.encode(), flat, len(pairs), v, ctypes.byref(flops), ctypes.byref(nodes), ctypes.byref(secs))
+    if rc != 0:
+        _raise(H, rc)
+    return complex(v[0], v[1]), flops.value, nodes.value, secs.value
+
+
+def export_plan_linegraph(qasm, measure, ordering, reduce=True):
+    """-> (input_ranks, steps, inputs, flops): host bookkeeping only (no device), ready for Engine.plan(...)."""
+    H = host_library()
+    p = _QthPlan()
+    rc = H.qth_export_plan_linegraph(qasm.encode(), measure.encode(), ordering.encode(), 1 if reduce else 0, ctypes.byref(p))
+    if rc != 0:
+        _raise(H, rc)
+    ranks = [p.inputRanks[i] for i in range(p.nInputs)]
+    inputs = []
+    for i, r in enumerate(ranks):
+        off = p.inputOffsets[i]
+        arr = np.ctypeslib.as_array(p.inputData, shape=(2 * (off + 4 ** r),))[2 * off:]
+        inputs.append(arr.copy().view(np.complex128))
+    steps = []
+    for i in range(p.nSteps):
+        s = p.steps[i]
+        steps.append((s.a, s.b, [s.pos_a[j] for j in range(s.k)], [s.pos_b[j] for j in range(s.k)]))
+    return ranks, steps, inputs, p.flops

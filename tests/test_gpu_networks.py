@@ -1,0 +1,113 @@
+"""GPU parity, network level: the C++ host mirror (Network / LineGraph / ContractionTools on the B200 engine) and
+the compiled-plan path of the C ABI against the golden values produced by the unmodified reference
+(tests/golden/networks.json; tolerance from BASELINE.json north_star: |d| <= 1e-10 * max(|ref|, 1))."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_paths, plan_file
+import qtorch_b200 as qt
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+NETS = json.load(open(os.path.join(GOLDEN, "networks.json")))
+SMALL = sorted(n for n in NETS if n != "qaoa30_z27z29")
+TOL = 1e-10
+
+
+def _close(val, ref):
+    ref = complex(ref[0], ref[1])
+    return abs(val - ref) <= TOL * max(abs(ref), 1.0)
+
+
+def _run(name, tmp_path, extra_env=None, steps=False):
+    rec = NETS[name]
+    cwd, qasm, meas, ordering = golden_paths(rec)
+    if rec["method"] == "lg":
+        args = ["lg+steps" if steps else "lg", qasm, meas, ordering, rec["reduce"]]
+    else:
+        args = ["seq+steps" if steps else "seq", qasm, meas, plan_file(rec, tmp_path)]
+    return rec, qt.run_harness(args, cwd=cwd, extra_env=extra_env, timeout=600)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_network_value_matches_reference(built, name, tmp_path):
+    rec, out = _run(name, tmp_path)
+    assert "exception" not in out, out.get("exception")
+    val = complex(float(out["value"][0]), float(out["value"][1]))
+    assert _close(val, rec["value"]), (val, rec["value"])
+    assert out["plan"] == rec["plan"] and int(out["flops"][0]) == rec["flops"]
+
+
+@pytest.mark.parametrize("name", ["qft8_X8", "qaoa20_node1_m125", "ghz64_zeros", "two_pairs_0011"])
+def test_network_value_without_micro_grouping(built, name, tmp_path):
+    """every step as its own launch (QTB_NO_MICRO) must give the same answer as the grouped executor"""
+    rec, out = _run(name, tmp_path, extra_env={"QTB_NO_MICRO": "1"})
+    val = complex(float(out["value"][0]), float(out["value"][1]))
+    assert _close(val, rec["value"]), (val, rec["value"])
+
+
+def test_plan_api_against_oracle(engine):
+    """qtb_plan_*: a random tree of contractions (micro + big steps mixed), host inputs in, result out"""
+    rng = np.random.default_rng(42)
+    ranks = [3, 4, 2, 5, 6, 1, 7, 8]
+    inputs = [rng.standard_normal(4 ** r) + 1j * rng.standard_normal(4 ** r) for r in ranks]
+    # (a, b, posA, posB): ids >= len(ranks) are results
+    steps = [
+        (0, 1, [0, 2], [1, 3]),          # 3x4 k2 -> rank 3   id 8
+        (2, 8, [1], [0]),                # 2x3 k1 -> rank 3   id 9
+        (3, 4, [0, 4], [5, 2]),          # 5x6 k2 -> rank 7   id 10
+        (5, 10, [0], [3]),               # 1x7 k1 -> rank 6   id 11
+        (6, 7, [1, 3, 5], [0, 4, 7]),    # 7x8 k3 -> rank 9   id 12  (DMMA tiles)
+        (11, 12, [0, 2, 4], [8, 1, 3]),  # 6x9 k3 -> rank 9   id 13
+        (9, 13, [0, 1, 2], [2, 5, 7]),   # 3x9 k3 -> rank 6   id 14
+    ]
+    plan = engine.plan(ranks, steps)
+    out = plan.run_host(inputs)
+    tens = list(inputs)
+    rk = list(ranks)
+    O.lib().qto_set_threads(16)
+    units = 0
+    for a, b, pa, pb in steps:
+        tens.append(O.contract(tens[a], rk[a], tens[b], rk[b], pa, pb))
+        rk.append(rk[a] + rk[b] - 2 * len(pa))
+        units += 4 ** (rk[-1] + len(pa))
+    assert plan.output_rank == rk[-1] and plan.units == units
+    assert np.abs(out - tens[-1]).max() <= 1e-11 * np.abs(tens[-1]).max()
+    # device-resident replay gives the same bits every time (deterministic kernels)
+    plan.upload_inputs(inputs)
+    plan.run_device(); a1 = plan.read_output()
+    plan.run_device(); a2 = plan.read_output()
+    assert np.array_equal(a1.view(np.float64), a2.view(np.float64)) and np.array_equal(a1.view(np.float64), out.view(np.float64))
+    plan.destroy()
+
+
+def test_plan_rejects_reuse_of_contracted_tensor(engine):
+    with pytest.raises(qt.EngineError):
+        engine.plan([1, 1, 1], [(0, 1, [0], [0]), (0, 2, [0], [0])])
+
+
+def test_config2_qaoa30_term_full_size(built, tmp_path):
+    """BASELINE config 2 at full size: the <Z27 Z29> term of 4regRand30Node5-p1 on the frozen ordering --
+    6.9e10 units, four rank-14 DMMA steps and a 268M-term inner product -- against the reference's value
+    (-0.26965021147727669, 797 s on 8 CPU threads)."""
+    rec, out = _run("qaoa30_z27z29", tmp_path)
+    assert "exception" not in out, out.get("exception")
+    val = complex(float(out["value"][0]), float(out["value"][1]))
+    assert _close(val, rec["value"]), (val, rec["value"])
+    assert out["plan"] == rec["plan"] and int(out["flops"][0]) == rec["flops"] == 69351174176
+
+
+def test_config2_trace_is_one_full_size(built, tmp_path):
+    """size-independent property on the same 30-qubit plan: measuring nothing (all qubits traced) must give
+    tr(rho) = 1 -- exercises every big kernel with a different set of rank-1 caps"""
+    rec = NETS["qaoa30_z27z29"]
+    cwd, qasm, _, ordering = golden_paths(rec)
+    meas = os.path.join(str(tmp_path), "allT.txt")
+    open(meas, "w").write(" ".join(["T"] * 30) + "\n")
+    out = qt.run_harness(["lg", qasm, meas, ordering, 1], cwd=cwd, timeout=600)
+    val = complex(float(out["value"][0]), float(out["value"][1]))
+    assert abs(val - 1.0) <= 1e-10, val
+    assert out["plan"] == rec["plan"]
