@@ -94,3 +94,21 @@ def test_parser_error_behaviour(built, tmp_path):
     assert qt.run_harness(["stoch", bad, meas], plan_only=True)["exception"] == "Invalid File Format."
     out = qt.run_harness(["stoch", os.path.join(str(tmp_path), "missing.qasm"), meas], plan_only=True)
     assert out["exception"] == "Invalid Input or Output File Path"
+
+
+@pytest.mark.parametrize("name", ["qft8_X8", "testJW_YXXY", "rand6_rxz_ZI", "cat8_ones", "qaoa20_node5_m125", "ghz64_zeros"])
+def test_exported_plan_evaluated_by_oracle_matches_reference_value(built, name):
+    """host mirror (parser, gate tensors, ReduceCircuit, LGContract bookkeeping) + CPU oracle arithmetic reproduce the
+    reference's value: pins everything except the CUDA kernels without a GPU"""
+    from qtorch_b200 import host_api
+    rec = NETS[name]
+    cwd, qasm, meas, ordering = golden_paths(rec)
+    ranks, steps, inputs, flops = host_api.export_plan_linegraph(os.path.join(cwd, qasm), meas, ordering, bool(rec["reduce"]))
+    assert flops == rec["flops"] and len(steps) == len(rec["plan"])
+    O.lib().qto_set_threads(8)
+    t, rk = list(inputs), list(ranks)
+    for a, b, pa, pb in steps:
+        t.append(O.contract(t[a], rk[a], t[b], rk[b], pa, pb))
+        rk.append(rk[a] + rk[b] - 2 * len(pa))
+    ref = complex(*rec["value"])
+    assert abs(complex(t[-1][0]) - ref) <= 1e-12 * max(1.0, abs(ref))
