@@ -48,14 +48,21 @@ struct GettChoice { int cfg; bool swap; };      // cfg: 0 C1/TK16 1 C1/TK4 2 C2/
 typedef void (*GettKernel)(const GettParams);
 struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; };
 // C1: 128x64 tile, compute-bound big x big;  C2: 256x16;  C3: 256x8 (N <= 4 padded) -- streaming
-static GettInst g_gett[6] = {
+static GettInst g_gett[7] = {
     {k_gett<4, 2, 4, 4, 16, 3>, 128, 64, 16, 256, GettCfg<4, 2, 4, 4, 16, 3>::SMEM, 1},
     {k_gett<4, 2, 4, 4, 4, 4>, 128, 64, 4, 256, GettCfg<4, 2, 4, 4, 4, 4>::SMEM, 1},
     {k_gett<8, 1, 4, 2, 16, 3>, 256, 16, 16, 256, GettCfg<8, 1, 4, 2, 16, 3>::SMEM, 1},
     {k_gett<8, 1, 4, 2, 4, 4>, 256, 16, 4, 256, GettCfg<8, 1, 4, 2, 4, 4>::SMEM, 1},
     {k_gett<8, 1, 4, 1, 16, 3>, 256, 8, 16, 256, GettCfg<8, 1, 4, 1, 16, 3>::SMEM, 1},
     {k_gett<8, 1, 4, 1, 4, 4>, 256, 8, 4, 256, GettCfg<8, 1, 4, 1, 4, 4>::SMEM, 1},
+    // C1 with 16 warps of 32x16 (4 warps per scheduler hide the LDS / DMMA-dependency latencies)
+    {k_gett<4, 4, 4, 2, 16, 3>, 128, 64, 16, 512, GettCfg<4, 4, 4, 2, 16, 3>::SMEM, 1},
 };
+static int c1_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_GETT_C1"); v = e ? atoi(e) : 0; }
+    return v;
+}
 
 static int ilog2i(unsigned long long v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
 
@@ -112,7 +119,7 @@ static int choose_kind(const StepGeom &g, GettChoice &gc) {
     if (!force_generic() && bigFree >= 4 && g.k >= 1) {
         gc.swap = g.nfb > g.nfa;
         const int tk4 = (g.k == 1) ? 1 : 0;
-        if (smallFree >= 3) gc.cfg = 0 + tk4;
+        if (smallFree >= 3) gc.cfg = (tk4 == 0 && c1_variant() == 1) ? 6 : 0 + tk4;
         else if (smallFree == 2) gc.cfg = 2 + tk4;
         else gc.cfg = 4 + tk4;
         return KIND_GETT;
@@ -334,6 +341,24 @@ static const unsigned REDUCE_MAX_BLOCKS = 148 * 8;
 static int launch_reduce(qtb_ctx *ctx, const StepGeom &g, const double2 *A, const double2 *B, double2 *C, cudaStream_t s) {
     ReduceParams p;
     build_reduce(g, A, B, C, ctx->reduceScratch, p);
+    if (g.rC == 0) {
+        // inner product: each operand streamed in its own memory order, permutation undone in shared memory
+        DotParams d;
+        memset(&d, 0, sizeof(d));
+        d.A = A; d.B = B; d.partial = ctx->reduceScratch; d.nTiles = p.nTiles; d.kbits = p.kbits;
+        memcpy(d.shA, p.shA, 32); memcpy(d.shB, p.shB, 32);
+        int ia[8], ib[8];
+        for (int j = 0; j < 8; j++) ia[j] = ib[j] = j;
+        std::sort(ia, ia + 8, [&](int x, int y) { return p.shA[x] < p.shA[y]; });
+        std::sort(ib, ib + 8, [&](int x, int y) { return p.shB[x] < p.shB[y]; });
+        for (int j = 0; j < 8; j++) { d.permA[j] = (uint8_t)ia[j]; d.permB[j] = (uint8_t)ib[j]; }
+        const unsigned grid = std::min<unsigned>((p.nTiles + QTB_DOT_T - 1) / QTB_DOT_T, std::min<unsigned>(REDUCE_MAX_BLOCKS, (unsigned)ctx->numSMs * 6));
+        k_dot<<<grid, 256, 0, s>>>(d);
+        k_reduce_final<1><<<1, 32, 0, s>>>(ctx->reduceScratch, C, grid);
+        CU(cudaGetLastError());
+        ctx->stats.launches += 2;
+        return QTB_OK;
+    }
     const unsigned grid = std::min<unsigned>(p.nTiles, std::min<unsigned>(REDUCE_MAX_BLOCKS, (unsigned)ctx->numSMs * 8));
     switch (g.rC) {
         case 0: k_reduce<1><<<grid, 256, 0, s>>>(p); k_reduce_final<1><<<1, 32, 0, s>>>(p.partial, C, grid); break;

@@ -206,17 +206,27 @@ __global__ void __launch_bounds__(WX *WY * 32, 1) k_gett(const GettParams p) {
             for (int i = 0; i < FX; i++) xf[i] = xs[(kk * 4 + t) * LDX + wx0 + i * 8 + g];
 #pragma unroll
             for (int j = 0; j < FY; j++) yf[j] = ys[(kk * 4 + t) * LDY + wy0 + j * 8 + g];
+            // four passes over the FX x FY accumulator tiles, one per real product: consecutive DMMAs never
+            // touch the same accumulator (a dependent pair is FX*FY issues apart)
+            double nxi[FX];
 #pragma unroll
-            for (int i = 0; i < FX; i++) {
-                const double nxi = dneg(xf[i].y);
+            for (int i = 0; i < FX; i++) nxi[i] = dneg(xf[i].y);
 #pragma unroll
-                for (int j = 0; j < FY; j++) {
-                    dmma884(accR[i][j][0], accR[i][j][1], xf[i].x, yf[j].x);
-                    dmma884(accI[i][j][0], accI[i][j][1], xf[i].x, yf[j].y);
-                    dmma884(accR[i][j][0], accR[i][j][1], nxi, yf[j].y);
-                    dmma884(accI[i][j][0], accI[i][j][1], xf[i].y, yf[j].x);
-                }
-            }
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma884(accR[i][j][0], accR[i][j][1], xf[i].x, yf[j].x);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].x, yf[j].y);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma884(accR[i][j][0], accR[i][j][1], nxi[i], yf[j].y);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].y, yf[j].x);
         }
 
         if (ch == nChunks - 1) {

@@ -63,6 +63,66 @@ __global__ void __launch_bounds__(256) k_reduce(const ReduceParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// rC = 0 (pure inner product with a digit-permuted second operand): both operands are read in their
+// OWN memory order (lanes follow each operand's contiguous bits -> 256-byte runs for A and for B) and
+// meet through shared memory, where the tile coordinate undoes the permutation.
+struct DotParams {
+    const double2 *A;
+    const double2 *B;
+    double2 *partial;
+    uint32_t nTiles;
+    uint8_t kbits;
+    uint8_t shA[32], shB[32];      // summed bit j (tile-coordinate order) -> bit position inside A / B
+    uint8_t permA[8], permB[8];    // thread bit j -> tile-coordinate bit, ordered by the operand's memory significance
+};
+
+__device__ __forceinline__ uint32_t dot_swz(uint32_t c) { return c ^ ((c >> 3) & 7u) ^ ((c >> 6) & 3u); }
+
+#define QTB_DOT_T 4
+__global__ void __launch_bounds__(256) k_dot(const DotParams p) {
+    __shared__ double2 sA[QTB_DOT_T][256], sB[QTB_DOT_T][256];
+    __shared__ double2 red[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t cA = 0, cB = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { cA |= ((tid >> j) & 1u) << p.permA[j]; cB |= ((tid >> j) & 1u) << p.permB[j]; }
+    const uint32_t oA = scatter32(cA, p.shA, 0, 8), oB = scatter32(cB, p.shB, 0, 8);
+    const uint32_t wA = dot_swz(cA), wB = dot_swz(cB), rd = dot_swz(tid);
+    const int hi = p.kbits - 8;
+    const double2 *__restrict__ A = p.A;
+    const double2 *__restrict__ B = p.B;
+    double accR = 0.0, accI = 0.0;
+    for (uint32_t base = blockIdx.x * QTB_DOT_T; base < p.nTiles; base += gridDim.x * QTB_DOT_T) {
+        double2 a[QTB_DOT_T], b[QTB_DOT_T];
+#pragma unroll
+        for (int u = 0; u < QTB_DOT_T; u++) {
+            const uint32_t tile = base + u;
+            if (tile < p.nTiles) {
+                a[u] = A[(size_t)scatter32(tile, p.shA, 8, hi) + oA];
+                b[u] = B[(size_t)scatter32(tile, p.shB, 8, hi) + oB];
+            } else {
+                a[u] = make_double2(0.0, 0.0); b[u] = make_double2(0.0, 0.0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < QTB_DOT_T; u++) { sA[u][wA] = a[u]; sB[u][wB] = b[u]; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < QTB_DOT_T; u++) cmac(accR, accI, sA[u][rd], sB[u][rd]);
+        __syncthreads();
+    }
+    const double r = warp_sum(accR), i = warp_sum(accI);
+    if (lane == 0) red[warp] = make_double2(r, i);
+    __syncthreads();
+    if (tid == 0) {
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { sr += red[w].x; si += red[w].y; }
+        p.partial[blockIdx.x] = make_double2(sr, si);
+    }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(32 * NC) k_reduce_final(const double2 *__restrict__ partial, double2 *C, uint32_t nBlocks) {
     const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
