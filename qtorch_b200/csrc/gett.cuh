@@ -8,7 +8,7 @@
 // (the operand with the larger free dimension), so D is C or C^T; every operand and the output are
 // addressed through per-bit shift tables, so any leg placement is legal.
 //
-// Structure (one persistent CTA per SM, 8 warps):
+// Structure (one persistent CTA per SM: 8 math warps + 1 producer warp, mbarrier full/empty ring):
 //   * tile gather  : 16-byte cp.async.cg (LDGSTS) per element, lanes ordered along the operand's
 //                    memory-contiguous bits (host-computed bit permutation) -> >= 64 B runs always
 //   * pipeline     : STAGES-deep ring over the FLAT (tile, k-chunk) sequence, so the next tile's
@@ -61,34 +61,66 @@ __device__ __forceinline__ uint32_t scatter_bits(uint32_t v, const uint8_t *sh, 
 
 template <int WX, int WY, int FX, int FY, int TK, int STAGES>
 struct GettCfg {
-    static constexpr int NT = WX * WY * 32;
+    static constexpr int NW = WX * WY;                        // math warps; one more warpgroup (4 warps) produces
+    static constexpr int NPT = 128;                           // producer threads
+    static constexpr int NT = NW * 32 + NPT;
+    // register split (setmaxnreg): the per-scheduler total must stay within what the CTA was launched with
+    // (8 math warps: 3 warps/scheduler x 168 = 504 = 2 x 224 + 56;  16 math warps: 5 x 96 = 480 = 4 x 104 + 64)
+    static constexpr int MATH_REGS = NW == 8 ? 224 : 104, PROD_REGS = NW == 8 ? 56 : 64;
     static constexpr int TM = WX * FX * 8, TN = WY * FY * 8;
     static constexpr int LDX = TM + 2, LDY = TN + 2;          // +2 (x16 B): conflict-free LDS.128 fragments
     static constexpr int XS = TK * LDX, YS = TK * LDY;        // elements per stage
     static constexpr int STAGE_ELEMS = XS + YS;
-    static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 64; // uint32 tables
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 16 + TAB * 4;
-    static constexpr int XSLOTS = (TM * TK + NT - 1) / NT, YSLOTS = (TN * TK + NT - 1) / NT;
+    static constexpr int XROUNDS = (TM * TK + NPT - 1) / NPT, YROUNDS = (TN * TK + NPT - 1) / NPT;
+    static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 2 * XROUNDS + 2 * YROUNDS;   // uint32 tables
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 16 + TAB * 4 + 2 * STAGES * 8 + 16;
 };
 
 __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 
+// ---- mbarrier helpers (CTA scope) ---------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE;\n"
+        " bra WAIT_LOOP;\n"
+        "DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+// arrive on `bar` once every cp.async issued so far by this thread has landed (count pre-charged at init)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Warp-specialised: warps 0..NW-1 do LDS + DMMA + the C stores, the last warpgroup only gathers tiles (cp.async)
+// and signals "full" mbarriers; math warps hand stages back through "empty" mbarriers.  The math pipe never waits
+// for address arithmetic or load issue, and the gather of the next tiles proceeds under the epilogue stores.
 template <int WX, int WY, int FX, int FY, int TK, int STAGES>
-__global__ void __launch_bounds__(WX *WY * 32, 1) k_gett(const GettParams p) {
+__global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams p) {
     using Cfg = GettCfg<WX, WY, FX, FY, TK, STAGES>;
-    constexpr int NT = Cfg::NT, TM = Cfg::TM, TN = Cfg::TN, LDX = Cfg::LDX, LDY = Cfg::LDY;
+    constexpr int NW = Cfg::NW, NT = Cfg::NT, TM = Cfg::TM, TN = Cfg::TN, LDX = Cfg::LDX, LDY = Cfg::LDY;
     constexpr int TMB = ilog2(TM), TNB = ilog2(TN), TKB = ilog2(TK);
-    constexpr int XSLOTS = Cfg::XSLOTS, YSLOTS = Cfg::YSLOTS;
+    constexpr int XROUNDS = Cfg::XROUNDS, YROUNDS = Cfg::YROUNDS;
 
     extern __shared__ __align__(16) uint8_t smemRaw[];
     double2 *stages = reinterpret_cast<double2 *>(smemRaw);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smemRaw + (size_t)STAGES * Cfg::STAGE_ELEMS * 16);
     uint32_t *tXx = tab, *tCx = tXx + TM, *tYy = tCx + TM, *tCy = tYy + TN, *tXk = tCy + TN, *tYk = tXk + TK;
-    uint32_t *dXo = tYk + TK, *dXs = dXo + 16, *dYo = dXs + 16, *dYs = dYo + 16;   // per-slot-round deltas
+    uint32_t *dXo = tYk + TK, *dXs = dXo + XROUNDS, *dYo = dXs + XROUNDS, *dYs = dYo + YROUNDS;   // per-round deltas
+    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(dYs + YROUNDS) + 7) & ~(uintptr_t)7);
+    const uint32_t barBase = (uint32_t)__cvta_generic_to_shared(bars);        // full[s] = barBase + 8 s, empty[s] = full + 8 STAGES
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int wx0 = (warp % WX) * (FX * 8), wy0 = (warp / WX) * (FY * 8);
     const uint32_t nyValid = p.nyValid;
 
     // ---- one-time tables: tile-local coordinate -> element offset
@@ -107,10 +139,13 @@ __global__ void __launch_bounds__(WX *WY * 32, 1) k_gett(const GettParams p) {
     }
     // zero the operand ring once: padded y columns (N < TN) are never written again
     for (int i = tid; i < STAGES * Cfg::STAGE_ELEMS; i += NT) stages[i] = make_double2(0.0, 0.0);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(barBase + 8 * s, Cfg::NPT); mbar_init(barBase + 8 * (STAGES + s), NW); }
+    }
     __syncthreads();
 
-    // slot id e = tid + r*NT  ->  tile coordinate via the load-order permutation; the contribution
-    // of the r bits is CTA-uniform, so only the tid part lives in registers.
+    // slot id e = ptid + 128*r  ->  tile coordinate via the load-order permutation (bits follow the operand's
+    // memory significance); offsets are sums over disjoint bit contributions, so off(e) = off(lane) + off(32 r)
     auto coordOf = [&](uint32_t e, const uint8_t *perm, int nbits) {
         uint32_t w = 0;
         for (int j = 0; j < nbits; j++) w |= ((e >> j) & 1u) << perm[j];
@@ -119,29 +154,18 @@ __global__ void __launch_bounds__(WX *WY * 32, 1) k_gett(const GettParams p) {
     constexpr int XEB = TMB + TKB;
     const int yeb = p.nyBits + TKB;                     // valid Y-tile slot bits
     const uint32_t nYElems = 1u << yeb;
-    uint32_t xOff0, xSm0, yOff0 = 0, ySm0 = 0;
-    {
-        const uint32_t w = coordOf(tid & ((1u << XEB) - 1), p.permX, XEB);
+    for (int r = tid; r < XROUNDS; r += NT) {
+        const uint32_t w = coordOf((uint32_t)r << 7, p.permX, XEB);
         const uint32_t xl = w & (TM - 1), kl = w >> TMB;
-        xOff0 = tXx[xl] + tXk[kl];
-        xSm0 = (kl * LDX + xl) * 16;
-        const uint32_t wy = coordOf(tid & (nYElems - 1), p.permY, yeb);
-        const uint32_t yl = wy & (TN - 1), kly = wy >> TNB;
-        yOff0 = tYy[yl] + tYk[kly];
-        ySm0 = (Cfg::XS + kly * LDY + yl) * 16;
+        dXo[r] = tXx[xl] + tXk[kl];
+        dXs[r] = (kl * LDX + xl) * 16;
     }
-    if (tid < XSLOTS) {
-        const uint32_t w = coordOf((uint32_t)tid * NT & ((1u << XEB) - 1), p.permX, XEB);
-        const uint32_t xl = w & (TM - 1), kl = w >> TMB;
-        dXo[tid] = tXx[xl] + tXk[kl];
-        dXs[tid] = (kl * LDX + xl) * 16;
-    }
-    if (tid < YSLOTS) {
-        const uint32_t e = (uint32_t)tid * NT;
+    for (int r = tid; r < YROUNDS; r += NT) {
+        const uint32_t e = (uint32_t)r << 7;
         const uint32_t wy = e < nYElems ? coordOf(e, p.permY, yeb) : 0u;
         const uint32_t yl = wy & (TN - 1), kly = wy >> TNB;
-        dYo[tid] = tYy[yl] + tYk[kly];
-        dYs[tid] = (kly * LDY + yl) * 16;
+        dYo[r] = tYy[yl] + tYk[kly];
+        dYs[r] = (kly * LDY + yl) * 16;
     }
     __syncthreads();
 
@@ -150,54 +174,65 @@ __global__ void __launch_bounds__(WX *WY * 32, 1) k_gett(const GettParams p) {
     const uint32_t myTiles = blockIdx.x < nTiles ? (nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t total = myTiles * nChunks;
 
-    auto issue = [&](uint32_t q) {
-        // flat pipeline index q -> (tile, chunk)
-        const uint32_t ti = q / nChunks, ch = q - ti * nChunks;
-        const uint32_t tile = blockIdx.x + ti * gridDim.x;
-        const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
-        const uint32_t stage = q % STAGES;
-        const uint32_t chX = scatter_bits(ch, p.shXk, TKB, p.kbits - TKB);
-        const uint32_t chY = scatter_bits(ch, p.shYk, TKB, p.kbits - TKB);
-        const double2 *gx = p.X + scatter_bits(tx, p.shXx, TMB, p.xbits - TMB) + chX + xOff0;
-        const double2 *gy = p.Y + scatter_bits(ty, p.shYy, p.nyBits, p.ybits - p.nyBits) + chY + yOff0;
-        const uint32_t sb = smemBase + stage * (Cfg::STAGE_ELEMS * 16);
-#pragma unroll
-        for (int r = 0; r < XSLOTS; r++) {
-            if (XSLOTS * NT == TM * TK || tid + r * NT < TM * TK) cp_async16(sb + xSm0 + dXs[r], gx + dXo[r]);
+    if (warp >= NW) {
+        // ================= producer warpgroup =================
+        setmaxnreg_dec<Cfg::PROD_REGS>();
+        const uint32_t ptid = tid - NW * 32;
+        uint32_t xOff0, xSm0, yOff0, ySm0;
+        {
+            const uint32_t w = coordOf(ptid & ((1u << XEB) - 1), p.permX, XEB);
+            const uint32_t xl = w & (TM - 1), kl = w >> TMB;
+            xOff0 = tXx[xl] + tXk[kl];
+            xSm0 = (kl * LDX + xl) * 16;
+            const uint32_t wy = coordOf(ptid & (nYElems - 1), p.permY, yeb);
+            const uint32_t yl = wy & (TN - 1), kly = wy >> TNB;
+            yOff0 = tYy[yl] + tYk[kly];
+            ySm0 = (Cfg::XS + kly * LDY + yl) * 16;
         }
-#pragma unroll
-        for (int r = 0; r < YSLOTS; r++) {
-            if ((uint32_t)(tid + r * NT) < nYElems) cp_async16(sb + ySm0 + dYs[r], gy + dYo[r]);
+        const int yRounds = (int)((nYElems + Cfg::NPT - 1) / Cfg::NPT);
+        const bool yLane = ptid < nYElems;
+        const bool xLane = ptid < (uint32_t)(TM * TK);
+        uint32_t ti = 0, ch = 0;
+        for (uint32_t q = 0; q < total; q++) {
+            const uint32_t stage = q % STAGES, round = q / STAGES;
+            if (round > 0) mbar_wait(barBase + 8 * (STAGES + stage), (round - 1) & 1);
+            const uint32_t tile = blockIdx.x + ti * gridDim.x;
+            const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
+            const double2 *gx = p.X + scatter_bits(tx, p.shXx, TMB, p.xbits - TMB) + scatter_bits(ch, p.shXk, TKB, p.kbits - TKB) + xOff0;
+            const double2 *gy = p.Y + scatter_bits(ty, p.shYy, p.nyBits, p.ybits - p.nyBits) + scatter_bits(ch, p.shYk, TKB, p.kbits - TKB) + yOff0;
+            const uint32_t sb = smemBase + stage * (Cfg::STAGE_ELEMS * 16);
+            if (xLane) {
+#pragma unroll 8
+                for (int r = 0; r < XROUNDS; r++) cp_async16(sb + xSm0 + dXs[r], gx + dXo[r]);
+            }
+            if (yLane) {
+#pragma unroll 4
+                for (int r = 0; r < yRounds; r++) cp_async16(sb + ySm0 + dYs[r], gy + dYo[r]);
+            }
+            cp_async_mbar_arrive(barBase + 8 * stage);
+            if (++ch == nChunks) { ch = 0; ++ti; }
         }
-    };
-
-    // NOTE on the slot decomposition: slot e = tid + r*NT with NT a power of two, so the bits of e
-    // split into the tid bits and the r bits; offsets are sums over disjoint bit contributions, hence
-    // off(e) = off(tid) + off(r*NT).  When the tile has fewer than NT elements the tid is masked.
-
-    double accR[FX][FY][2], accI[FX][FY][2];
-
-#pragma unroll 1
-    for (uint32_t q = 0; q < (uint32_t)(STAGES - 1); q++) {
-        if (q < total) issue(q);
-        cp_async_commit();
+        cp_async_wait<0>();
+        return;
     }
 
+    // ================= math warps =================
+    setmaxnreg_inc<Cfg::MATH_REGS>();
+    const int g = lane >> 2, t = lane & 3;
+    const int wx0 = (warp % WX) * (FX * 8), wy0 = (warp / WX) * (FY * 8);
+    double accR[FX][FY][2], accI[FX][FY][2];
+    uint32_t ti = 0, ch = 0;
 #pragma unroll 1
     for (uint32_t q = 0; q < total; q++) {
-        const uint32_t ti = q / nChunks, ch = q - ti * nChunks;
         if (ch == 0) {
 #pragma unroll
             for (int i = 0; i < FX; i++)
 #pragma unroll
                 for (int j = 0; j < FY; j++) { accR[i][j][0] = accR[i][j][1] = accI[i][j][0] = accI[i][j][1] = 0.0; }
         }
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        if (q + STAGES - 1 < total) issue(q + STAGES - 1);
-        cp_async_commit();
-
-        const double2 *xs = stages + (size_t)(q % STAGES) * Cfg::STAGE_ELEMS;
+        const uint32_t stage = q % STAGES;
+        mbar_wait(barBase + 8 * stage, (q / STAGES) & 1);
+        const double2 *xs = stages + (size_t)stage * Cfg::STAGE_ELEMS;
         const double2 *ys = xs + Cfg::XS;
 #pragma unroll
         for (int kk = 0; kk < TK / 4; kk++) {
@@ -228,6 +263,9 @@ __global__ void __launch_bounds__(WX *WY * 32, 1) k_gett(const GettParams p) {
 #pragma unroll
                 for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].y, yf[j].x);
         }
+        // stage consumed: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(barBase + 8 * (STAGES + stage));
 
         if (ch == nChunks - 1) {
             const uint32_t tile = blockIdx.x + ti * gridDim.x;
@@ -243,9 +281,11 @@ __global__ void __launch_bounds__(WX *WY * 32, 1) k_gett(const GettParams p) {
                     if ((uint32_t)(y0 + 1) < nyValid) cb[ox + tCy[y0 + 1]] = make_double2(accR[i][j][1], accI[i][j][1]);
                 }
             }
+            ch = 0; ++ti;
+        } else {
+            ++ch;
         }
     }
-    cp_async_wait<0>();
 }
 
 }  // namespace qtb

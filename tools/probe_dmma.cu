@@ -1,0 +1,117 @@
+// tools/probe_dmma.cu -- what limits the complex DMMA inner loop of k_gett?  Variants of the fragment loop without
+// global traffic: v2 real FXxFY tile with distinct operands, v3 complex 4-pass pattern (the k_gett loop, interleaved
+// or pass-wise order), v4 = v3 + LDS.128 fragment loads from shared memory per k-step.
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int FX, int FY>
+__global__ void __launch_bounds__(512) v2(const double *in, double *out, int iters) {
+    double a[FX], b[FY], c[FX][FY][2];
+    for (int i = 0; i < FX; i++) a[i] = in[threadIdx.x + 32 * i];
+    for (int j = 0; j < FY; j++) b[j] = in[threadIdx.x + 32 * j + 512];
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) c[i][j][0] = c[i][j][1] = 0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+    double s = 0;
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) s += c[i][j][0] + c[i][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int FX, int FY, bool LDS, int ORDER>
+__global__ void __launch_bounds__(512) v3(const double2 *in, double *out, int iters) {
+    extern __shared__ double2 sm[];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = in[i];
+    __syncthreads();
+    double2 xf[FX], yf[FY];
+    double cr[FX][FY][2], ci[FX][FY][2];
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < FX; i++) xf[i] = sm[t * 130 + i * 8 + g];
+    for (int j = 0; j < FY; j++) yf[j] = sm[2100 + t * 66 + j * 8 + g];
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0;
+    for (int it = 0; it < iters; it++) {
+        if (LDS) {
+            const int kk = it & 3;
+#pragma unroll
+            for (int i = 0; i < FX; i++) xf[i] = sm[(kk * 4 + t) * 130 + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < FY; j++) yf[j] = sm[2100 + (kk * 4 + t) * 66 + j * 8 + g];
+        }
+        double nxi[FX];
+#pragma unroll
+        for (int i = 0; i < FX; i++) nxi[i] = -xf[i].y;
+        if (ORDER == 0) {
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) {
+                    dmma(cr[i][j][0], cr[i][j][1], xf[i].x, yf[j].x);
+                    dmma(ci[i][j][0], ci[i][j][1], xf[i].x, yf[j].y);
+                    dmma(cr[i][j][0], cr[i][j][1], nxi[i], yf[j].y);
+                    dmma(ci[i][j][0], ci[i][j][1], xf[i].y, yf[j].x);
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(cr[i][j][0], cr[i][j][1], xf[i].x, yf[j].x);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(ci[i][j][0], ci[i][j][1], xf[i].x, yf[j].y);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(cr[i][j][0], cr[i][j][1], nxi[i], yf[j].y);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(ci[i][j][0], ci[i][j][1], xf[i].y, yf[j].x);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) s += cr[i][j][0] + cr[i][j][1] + ci[i][j][0] + ci[i][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename F>
+static float time_ms(F f) {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    f(); CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) { CK(cudaEventRecord(e0)); f(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms; }
+    return best;
+}
+
+int main() {
+    double *in, *out; CK(cudaMalloc(&in, 1 << 20)); CK(cudaMalloc(&out, 1 << 24)); CK(cudaMemset(in, 0, 1 << 20));
+    const int nsm = 148, iters = 4000;
+    const size_t smem = 4096 * 16;
+    auto rep = [&](const char *name, int warps, int dm, float ms) {
+        double fl = 2.0 * 256 * dm * (double)iters * warps * nsm;
+        printf("{\"probe\":\"%s\",\"warps_per_sm\":%d,\"tflops\":%.2f,\"ms\":%.3f}\n", name, warps, fl / ms * 1e-9, ms);
+    };
+#define RUN3(FX, FY, L, O, NAME) \
+    CK(cudaFuncSetAttribute(v3<FX, FY, L, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    for (int w : {8, 16}) { float ms = time_ms([&] { v3<FX, FY, L, O><<<nsm, w * 32, smem>>>((const double2 *)in, out, iters); }); rep(NAME, w, 4 * FX * FY, ms); }
+    for (int w : {8, 16}) { float ms = time_ms([&] { v2<4, 4><<<nsm, w * 32>>>(in, out, iters); }); rep("v2_real_4x4_distinct_operands", w, 64, ms); }
+    for (int w : {8, 16}) { float ms = time_ms([&] { v2<4, 2><<<nsm, w * 32>>>(in, out, iters); }); rep("v2_real_4x2", w, 32, ms); }
+    RUN3(4, 4, false, 0, "v3_complex_4x4_interleaved_noLDS");
+    RUN3(4, 4, false, 1, "v3_complex_4x4_4pass_noLDS");
+    RUN3(4, 4, true, 1, "v4_complex_4x4_4pass_LDS");
+    RUN3(4, 2, false, 1, "v3_complex_4x2_4pass_noLDS");
+    RUN3(4, 2, true, 1, "v4_complex_4x2_4pass_LDS");
+    RUN3(2, 2, true, 1, "v4_complex_2x2_4pass_LDS");
+    return 0;
+}
