@@ -22,7 +22,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -61,32 +60,51 @@ def write_measure_file(directory, edge):
     return path
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe): one streaming
+    nvidia-smi process (-lms 100) started before and killed after."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.proc, self.path = index, None, None
 
-    def run(self):
-        while not self.stop_flag:
+    def start(self):
+        fd, self.path = tempfile.mkstemp(prefix="qtb_clocks_", suffix=".csv")
+        os.close(fd)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-            time.sleep(0.2)
+                self.proc.kill()
 
     def summary(self):
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        samples = []
+        if self.path and os.path.exists(self.path):
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 7:
+                    samples.append(f)
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = sorted(v for v in (num(s[0]) for s in samples) if v is not None)
+        mx = [v for v in (num(s[1]) for s in samples) if v is not None]
+        pw = [v for v in (num(s[2]) for s in samples) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "reasons": reasons, "samples": len(samples)}
 
 
 def cpu_reference_sample(threads, budget_units=3.0e8):
@@ -138,7 +156,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -221,8 +239,7 @@ def main():
         values_e2e.append(v)
     ms_e2e = eng.timer_stop()
     barrier()
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
     stats_e2e = eng.stats()
 
     # both paths must agree with each other (and with the golden term when it is among them)
@@ -256,7 +273,7 @@ def main():
             avg_ms = sum(r["ms"] for r in gett) / len(gett)
             flop = 8.0 * 4 ** 17                                   # 8 * 4^(rC+k), rC = 14, k = 3
             ach = flop / (avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "k_gett<4,2,4,4,16,3> (FP64 DMMA tiles, rank-14 steps)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
+            roof = {"bound": "tensor", "kernel": "k_gett<4,4,4,2,16,4> (warp-specialised FP64 DMMA tiles 128x64x16, the four rank-14 steps)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
                     "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "traffic": None, "launches_timed": len(gett), "avg_ms": avg_ms,
                     "share_of_step": sum(r["ms"] for r in gett) / total_ms,
                     "peak_source": "measured: tools/probe_fp64 DMMA m8n8k4 on this pool's B200 (profiles/r01_probe_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry"}

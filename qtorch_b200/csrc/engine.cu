@@ -50,17 +50,17 @@ struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; };
 // C1: 128x64 tile, compute-bound big x big;  C2: 256x16;  C3: 256x8 (N <= 4 padded) -- streaming
 static GettInst g_gett[7] = {
     {k_gett<4, 2, 4, 4, 16, 4>, 128, 64, 16, GettCfg<4, 2, 4, 4, 16, 4>::NT, GettCfg<4, 2, 4, 4, 16, 4>::SMEM, 1},
-    {k_gett<4, 2, 4, 4, 4, 4>, 128, 64, 4, GettCfg<4, 2, 4, 4, 4, 4>::NT, GettCfg<4, 2, 4, 4, 4, 4>::SMEM, 1},
+    {k_gett<4, 2, 4, 4, 4, 12>, 128, 64, 4, GettCfg<4, 2, 4, 4, 4, 12>::NT, GettCfg<4, 2, 4, 4, 4, 12>::SMEM, 1},
     {k_gett<8, 1, 4, 2, 16, 3>, 256, 16, 16, GettCfg<8, 1, 4, 2, 16, 3>::NT, GettCfg<8, 1, 4, 2, 16, 3>::SMEM, 1},
-    {k_gett<8, 1, 4, 2, 4, 4>, 256, 16, 4, GettCfg<8, 1, 4, 2, 4, 4>::NT, GettCfg<8, 1, 4, 2, 4, 4>::SMEM, 1},
+    {k_gett<8, 1, 4, 2, 4, 10>, 256, 16, 4, GettCfg<8, 1, 4, 2, 4, 10>::NT, GettCfg<8, 1, 4, 2, 4, 10>::SMEM, 1},
     {k_gett<8, 1, 4, 1, 16, 3>, 256, 8, 16, GettCfg<8, 1, 4, 1, 16, 3>::NT, GettCfg<8, 1, 4, 1, 16, 3>::SMEM, 1},
-    {k_gett<8, 1, 4, 1, 4, 4>, 256, 8, 4, GettCfg<8, 1, 4, 1, 4, 4>::NT, GettCfg<8, 1, 4, 1, 4, 4>::SMEM, 1},
+    {k_gett<8, 1, 4, 1, 4, 10>, 256, 8, 4, GettCfg<8, 1, 4, 1, 4, 10>::NT, GettCfg<8, 1, 4, 1, 4, 10>::SMEM, 1},
     // C1 with 16 math warps of 32x16
     {k_gett<4, 4, 4, 2, 16, 4>, 128, 64, 16, GettCfg<4, 4, 4, 2, 16, 4>::NT, GettCfg<4, 4, 4, 2, 16, 4>::SMEM, 1},
 };
 static int c1_variant() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("QTB_GETT_C1"); v = e ? atoi(e) : 0; }
+    if (v < 0) { const char *e = getenv("QTB_GETT_C1"); v = e ? atoi(e) : 1; }       // 1 = 16 math warps (default), 0 = 8
     return v;
 }
 

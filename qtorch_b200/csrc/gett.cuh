@@ -59,6 +59,26 @@ __device__ __forceinline__ uint32_t scatter_bits(uint32_t v, const uint8_t *sh, 
     return o;
 }
 
+// High (per-tile / per-chunk) index bits -> element offset through 7-bit lookup tables in shared memory: a
+// bit-by-bit scatter costs ~4 instructions per bit, which made the streaming tile shapes issue-bound.
+#define QTB_HT_PARTS 4
+#define QTB_HT_SIZE 128
+struct HiTab { uint32_t t[QTB_HT_PARTS][QTB_HT_SIZE]; };
+__device__ __forceinline__ void hitab_build(HiTab &tab, const uint8_t *sh, int first, int count, int tid, int nthreads) {
+    for (int idx = tid; idx < QTB_HT_PARTS * QTB_HT_SIZE; idx += nthreads) {
+        const int part = idx / QTB_HT_SIZE, v = idx % QTB_HT_SIZE;
+        const int lo = 7 * part, n = count - lo < 0 ? 0 : (count - lo > 7 ? 7 : count - lo);
+        tab.t[part][v] = scatter_bits((uint32_t)v, sh, first + lo, n);
+    }
+}
+__device__ __forceinline__ uint32_t hitab_lookup(const HiTab &tab, uint32_t v, int parts) {
+    uint32_t o = tab.t[0][v & 127u];
+    if (parts > 1) o += tab.t[1][(v >> 7) & 127u];
+    if (parts > 2) o += tab.t[2][(v >> 14) & 127u];
+    if (parts > 3) o += tab.t[3][(v >> 21) & 127u];
+    return o;
+}
+
 template <int WX, int WY, int FX, int FY, int TK, int STAGES>
 struct GettCfg {
     static constexpr int NW = WX * WY;                        // math warps; one more warpgroup (4 warps) produces
@@ -73,7 +93,7 @@ struct GettCfg {
     static constexpr int STAGE_ELEMS = XS + YS;
     static constexpr int XROUNDS = (TM * TK + NPT - 1) / NPT, YROUNDS = (TN * TK + NPT - 1) / NPT;
     static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 2 * XROUNDS + 2 * YROUNDS;   // uint32 tables
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 16 + TAB * 4 + 2 * STAGES * 8 + 16;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 16 + TAB * 4 + 2 * STAGES * 8 + 16 + 6 * sizeof(HiTab);
 };
 
 __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
@@ -118,6 +138,7 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
     uint32_t *tXx = tab, *tCx = tXx + TM, *tYy = tCx + TM, *tCy = tYy + TN, *tXk = tCy + TN, *tYk = tXk + TK;
     uint32_t *dXo = tYk + TK, *dXs = dXo + XROUNDS, *dYo = dXs + XROUNDS, *dYs = dYo + YROUNDS;   // per-round deltas
     uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(dYs + YROUNDS) + 7) & ~(uintptr_t)7);
+    HiTab *hi = reinterpret_cast<HiTab *>(bars + 2 * STAGES);     // [0] X by tile-x, [1] Y by tile-y, [2] X by chunk, [3] Y by chunk, [4] C by tile-x, [5] C by tile-y
     const uint32_t barBase = (uint32_t)__cvta_generic_to_shared(bars);        // full[s] = barBase + 8 s, empty[s] = full + 8 STAGES
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -137,6 +158,14 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         tXk[i] = scatter_bits(i, p.shXk, 0, TKB);
         tYk[i] = scatter_bits(i, p.shYk, 0, TKB);
     }
+    const int xHiBits = p.xbits - TMB, yHiBits = p.ybits - p.nyBits, kHiBits = p.kbits - TKB;
+    const int xParts = (xHiBits + 6) / 7, yParts = (yHiBits + 6) / 7, kParts = (kHiBits + 6) / 7;
+    hitab_build(hi[0], p.shXx, TMB, xHiBits, tid, NT);
+    hitab_build(hi[1], p.shYy, p.nyBits, yHiBits, tid, NT);
+    hitab_build(hi[2], p.shXk, TKB, kHiBits, tid, NT);
+    hitab_build(hi[3], p.shYk, TKB, kHiBits, tid, NT);
+    hitab_build(hi[4], p.shCx, TMB, xHiBits, tid, NT);
+    hitab_build(hi[5], p.shCy, p.nyBits, yHiBits, tid, NT);
     // zero the operand ring once: padded y columns (N < TN) are never written again
     for (int i = tid; i < STAGES * Cfg::STAGE_ELEMS; i += NT) stages[i] = make_double2(0.0, 0.0);
     if (tid == 0) {
@@ -198,8 +227,8 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
             if (round > 0) mbar_wait(barBase + 8 * (STAGES + stage), (round - 1) & 1);
             const uint32_t tile = blockIdx.x + ti * gridDim.x;
             const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
-            const double2 *gx = p.X + scatter_bits(tx, p.shXx, TMB, p.xbits - TMB) + scatter_bits(ch, p.shXk, TKB, p.kbits - TKB) + xOff0;
-            const double2 *gy = p.Y + scatter_bits(ty, p.shYy, p.nyBits, p.ybits - p.nyBits) + scatter_bits(ch, p.shYk, TKB, p.kbits - TKB) + yOff0;
+            const double2 *gx = p.X + hitab_lookup(hi[0], tx, xParts) + hitab_lookup(hi[2], ch, kParts) + xOff0;
+            const double2 *gy = p.Y + hitab_lookup(hi[1], ty, yParts) + hitab_lookup(hi[3], ch, kParts) + yOff0;
             const uint32_t sb = smemBase + stage * (Cfg::STAGE_ELEMS * 16);
             if (xLane) {
 #pragma unroll 8
@@ -270,7 +299,7 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         if (ch == nChunks - 1) {
             const uint32_t tile = blockIdx.x + ti * gridDim.x;
             const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
-            double2 *cb = p.C + scatter_bits(tx, p.shCx, TMB, p.xbits - TMB) + scatter_bits(ty, p.shCy, p.nyBits, p.ybits - p.nyBits);
+            double2 *cb = p.C + hitab_lookup(hi[4], tx, xParts) + hitab_lookup(hi[5], ty, yParts);
 #pragma unroll
             for (int i = 0; i < FX; i++) {
                 const uint32_t ox = tCx[wx0 + i * 8 + g];

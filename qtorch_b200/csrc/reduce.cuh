@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t dot_swz(uint32_t c) { return c ^ ((c >> 3) &
 __global__ void __launch_bounds__(256) k_dot(const DotParams p) {
     __shared__ double2 sA[QTB_DOT_T][256], sB[QTB_DOT_T][256];
     __shared__ double2 red[8];
+    __shared__ uint32_t hA[4][64], hB[4][64];      // tile-index bits -> offsets, 6 bits per table (k <= 16: 24 bits)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t cA = 0, cB = 0;
 #pragma unroll
@@ -90,6 +91,13 @@ __global__ void __launch_bounds__(256) k_dot(const DotParams p) {
     const uint32_t oA = scatter32(cA, p.shA, 0, 8), oB = scatter32(cB, p.shB, 0, 8);
     const uint32_t wA = dot_swz(cA), wB = dot_swz(cB), rd = dot_swz(tid);
     const int hi = p.kbits - 8;
+    {
+        const int part = tid >> 6, v = tid & 63, lo = 6 * part;
+        const int n = hi - lo < 0 ? 0 : (hi - lo > 6 ? 6 : hi - lo);
+        hA[part][v] = scatter32(v, p.shA, 8 + lo, n);
+        hB[part][v] = scatter32(v, p.shB, 8 + lo, n);
+    }
+    __syncthreads();
     const double2 *__restrict__ A = p.A;
     const double2 *__restrict__ B = p.B;
     double accR = 0.0, accI = 0.0;
@@ -99,8 +107,9 @@ __global__ void __launch_bounds__(256) k_dot(const DotParams p) {
         for (int u = 0; u < QTB_DOT_T; u++) {
             const uint32_t tile = base + u;
             if (tile < p.nTiles) {
-                a[u] = A[(size_t)scatter32(tile, p.shA, 8, hi) + oA];
-                b[u] = B[(size_t)scatter32(tile, p.shB, 8, hi) + oB];
+                const uint32_t t0 = tile & 63, t1 = (tile >> 6) & 63, t2 = (tile >> 12) & 63, t3 = (tile >> 18) & 63;
+                a[u] = A[(size_t)(hA[0][t0] + hA[1][t1] + hA[2][t2] + hA[3][t3]) + oA];
+                b[u] = B[(size_t)(hB[0][t0] + hB[1][t1] + hB[2][t2] + hB[3][t3]) + oB];
             } else {
                 a[u] = make_double2(0.0, 0.0); b[u] = make_double2(0.0, 0.0);
             }
