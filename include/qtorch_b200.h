@@ -113,6 +113,11 @@ int qtb_plan_output_rank(qtb_plan *plan);
  * Only for plans whose inputs all have rank <= 5 (gate / state / measurement tensors).                  */
 int qtb_plan_stage_inputs(qtb_ctx *ctx, qtb_plan *plan, int slot, const double *const *host_inputs);
 int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *plan, int slot);
+/* Grouped evaluation of n independent plans with scalar outputs (e.g. the 45 per-edge <ZiZj> networks of one QAOA
+ * objective evaluation, maxcut.cpp:171-198): all inputs are uploaded, plans that consist of micro-steps only run in
+ * ONE launch (one CTA per plan), the n scalars come back with one synchronisation.
+ * host_inputs[i] is plan i's array of input pointers; host_out receives n (re, im) pairs.                       */
+int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const double *const *const *host_inputs, double *host_out);
 /* sum_steps 4^(rC+k): the reference's getNumFloatOps() contribution of this plan (Network.h:884-885). */
 long long qtb_plan_units(qtb_plan *plan);
 /* Number of kernel launches one qtb_plan_run_device enqueues. */

@@ -90,8 +90,8 @@ def ref_harness(args, cwd=None, shipped=False, timeout=None, env=None):
         parts = line[2:].split()
         if not parts:
             continue
-        if parts[0] == "step":
-            out["step"].append(parts[1:])
+        if parts[0] in ("step", "term"):
+            out.setdefault(parts[0], []).append(parts[1:])
         else:
             out[parts[0]] = parts[1:]
     if p.returncode not in (0, 1):

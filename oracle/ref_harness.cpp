@@ -22,6 +22,9 @@
 //                                                   stops once `budget` units have been executed (bounded sample)
 //   stoch qasm measure threads                      ContractionTools::Contract(Stochastic), prints the plan
 //   user  qasm measure seqfile                      ContractUserDefinedSequenceOfWires
+//   maxcut graph.dgf p outdir b1..bp g1..gp         the body of F_p (src/maxcut.cpp:162-204) for fixed angles: per-edge
+//                                                   light-cone circuits written with the reference's own emitters
+//                                                   (outdir/term<i>.qasm), contracted stochastically, summed
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +34,7 @@
 #include <chrono>
 
 #include "ContractionTools.h"   // reference header (pulls Network.h, Node.h, LineGraph.h ...)
+#include "maxcut.h"             // reference QAOA helpers (ExtraData, circuit emitters); <nlopt.hpp> = oracle/stubs
 
 using namespace qtorch;
 typedef std::complex<double> cplx;
@@ -210,6 +214,35 @@ static int mode_user(int argc, char **argv) {
     return 0;
 }
 
+static int mode_maxcut(int argc, char **argv) {
+    const char *graph = argv[2];
+    const int p = atoi(argv[3]);
+    const std::string outdir = argv[4];
+    std::vector<double> bg(2 * p);
+    for (int i = 0; i < 2 * p; i++) bg[i] = atof(argv[5 + i]);
+    ExtraData e(p, graph);
+    double fp = 0.0;
+    printf("@@edges %zu\n", e.pairs.size());
+    for (size_t c = 0; c < e.pairs.size(); c++) {
+        const std::string qasm = outdir + "/term" + std::to_string(c) + ".qasm", meas = outdir + "/term" + std::to_string(c) + ".meas";
+        {
+            std::ofstream q(qasm), m(meas);
+            const int nq = e.qubitsNeeded[c];
+            q << nq << std::endl;
+            outputInitialPlusStateToFile(q, nq);
+            applyU_CsThenU_Bs(e.realIterations[c], e.p, bg, nq, q);
+            for (int i = 0; i < nq; i++) m << ((i == 0 || i == 1) ? "Z " : "T ");
+        }
+        ContractionTools qc(qasm, meas);
+        auto net = qc.Contract(Stochastic);
+        printf("@@term %zu %d %d %d %.17g %.17g %lld\n", c, e.pairs[c].first, e.pairs[c].second, e.qubitsNeeded[c], qc.GetFinalVal().real(),
+               qc.GetFinalVal().imag(), net->getNumFloatOps());
+        fp += 0.5 * (1.0 - qc.GetFinalVal().real());
+    }
+    printf("@@fp %.17g\n", fp);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { fprintf(stderr, "usage: ref_harness <mode> ...\n"); return 2; }
     std::string m = argv[1];
@@ -221,6 +254,7 @@ int main(int argc, char **argv) {
         if (m == "seq") return mode_seq(argc, argv);
         if (m == "stoch") return mode_stoch(argc, argv);
         if (m == "user") return mode_user(argc, argv);
+        if (m == "maxcut") return mode_maxcut(argc, argv);
     } catch (std::exception &e) {
         printf("@@exception %s\n", e.what());
         return 1;

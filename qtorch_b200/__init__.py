@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "qtb_tensor_alloc", "qtb_tensor_free", "qtb_tensor_rank", "qtb_tensor_device_ptr",
     "qtb_tensor_upload", "qtb_tensor_download", "qtb_read_scalar", "qtb_contract",
     "qtb_plan_create", "qtb_plan_destroy", "qtb_plan_run_host", "qtb_plan_upload_inputs",
-    "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_stage_inputs", "qtb_plan_run_device_slot", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
+    "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_stage_inputs", "qtb_plan_run_device_slot", "qtb_plans_run_batched", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
     "qtb_comm_unique_id", "qtb_comm_init", "qtb_comm_destroy", "qtb_allreduce_sum",
     "qtb_ctx_stats", "qtb_ctx_reset_stats", "qtb_ctx_timer_start", "qtb_ctx_timer_stop", "qtb_ctx_trace_enable", "qtb_ctx_trace_read",
 ]

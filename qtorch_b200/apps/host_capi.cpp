@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../host/qtorch.hpp"
+#include "../host/maxcut.h"
 
 static thread_local std::string g_err;
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -121,6 +122,62 @@ int qth_export_plan_linegraph(const char *qasm, const char *measure, const char 
     }
     device::Engine::SetPlanOnly(before);
     return rc;
+}
+
+// ---- QAOA term dispatcher (host/maxcut.h QaoaObjective) -------------------------------------------------------------
+void *qth_qaoa_create(const char *graphFile, int p, int rank, int world, int planTries) {
+    try {
+        ExtraData data(p, graphFile);
+        return new QaoaObjective(data, rank, world, nullptr, planTries);
+    } catch (std::exception &e) { g_err = e.what(); return nullptr; } catch (const char *m) { g_err = m; return nullptr; }
+}
+void qth_qaoa_destroy(void *h) { delete static_cast<QaoaObjective *>(h); }
+int qth_qaoa_num_owned(void *h) { return static_cast<int>(static_cast<QaoaObjective *>(h)->OwnedEdges().size()); }
+int qth_qaoa_owned_edges(void *h, int *out) {
+    const auto &o = static_cast<QaoaObjective *>(h)->OwnedEdges();
+    for (size_t i = 0; i < o.size(); i++) out[i] = o[i];
+    return static_cast<int>(o.size());
+}
+long long qth_qaoa_units(void *h) { return static_cast<QaoaObjective *>(h)->UnitsPerEvaluation(); }
+int qth_qaoa_launches(void *h) { return static_cast<QaoaObjective *>(h)->LaunchesPerEvaluation(); }
+// <ZZ> of every owned edge (re, im pairs) and this rank's partial F_p for the angles (beta_1..p, gamma_1..p)
+int qth_qaoa_evaluate(void *h, const double *betasGammas, int n, double *termsReIm, double *partialFp) {
+    try {
+        std::vector<double> bg(betasGammas, betasGammas + n);
+        const auto vals = static_cast<QaoaObjective *>(h)->EvaluateOwnedTerms(bg);
+        double fp = 0.0;
+        for (size_t i = 0; i < vals.size(); i++) {
+            if (termsReIm) { termsReIm[2 * i] = vals[i].real(); termsReIm[2 * i + 1] = vals[i].imag(); }
+            fp += 0.5 * (1.0 - vals[i].real());
+        }
+        if (partialFp) *partialFp = fp;
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// host-only (no device): light-cone circuit text + measurement string of one edge, straight from ExtraData
+int qth_maxcut_circuit_text(const char *graphFile, int p, int edge, const double *betasGammas, char *buf, int bufLen, int *numEdges, int *numQubits) {
+    try {
+        ExtraData data(p, graphFile);
+        if (numEdges) *numEdges = static_cast<int>(data.pairs.size());
+        if (edge < 0 || edge >= static_cast<int>(data.pairs.size())) return -1;
+        std::vector<double> bg(betasGammas, betasGammas + 2 * p);
+        std::ostringstream q;
+        const int nq = data.qubitsNeeded[edge];
+        if (numQubits) *numQubits = nq;
+        q << nq << std::endl;
+        outputInitialPlusStateToFile(q, nq);
+        applyU_CsThenU_Bs(data.realIterations[edge], data.p, bg, nq, q);
+        const std::string t = q.str();
+        if (buf && bufLen > 0) { strncpy(buf, t.c_str(), bufLen - 1); buf[bufLen - 1] = 0; }
+        return static_cast<int>(t.size());
+    } catch (std::exception &e) { g_err = e.what(); return -2; } catch (const char *m) { g_err = m; return -2; }
+}
+// circuit text the reference would write to input/tempMaxCut.qasm for this edge; returns the length
+int qth_qaoa_circuit_text(void *h, int edge, const double *betasGammas, int n, char *buf, int bufLen) {
+    std::vector<double> bg(betasGammas, betasGammas + n);
+    const std::string t = static_cast<QaoaObjective *>(h)->CircuitText(edge, bg);
+    if (buf && bufLen > 0) { strncpy(buf, t.c_str(), bufLen - 1); buf[bufLen - 1] = 0; }
+    return static_cast<int>(t.size());
 }
 
 }  // extern "C"

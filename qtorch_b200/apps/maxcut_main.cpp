@@ -1,0 +1,117 @@
+// qtorch_b200/apps/maxcut_main.cpp -- `maxcutQAOA <graph.dgf> <p> 0 <angle file> [max evaluations]` on the B200 engine.
+// Counterpart of /root/reference/src/maxcut.cpp:227-328, mode 0 (find the QAOA angles that maximise F_p).
+//  * The objective is the reference's F_p (maxcut.cpp:162-204) evaluated by QaoaObjective: per-edge light-cone
+//    networks planned once, all edges of this rank in one grouped launch per evaluation.
+//  * The reference maximises with NLopt's COBYLA (third-party, vendored, no stopping criterion set); NLopt is out of
+//    scope here, so a small derivative-free Nelder-Mead ascent with an evaluation cap takes its place.  Same start
+//    point (beta = 0.392699, gamma = 0.785399, maxcut.cpp:155-157); the angle file is rewritten after every
+//    evaluation like the reference does (maxcut.cpp:199-202).
+//  * Modes 1 and 2 (final bit-string sampler, maxcut.cpp:29-140) are not provided.
+#include <sys/stat.h>
+#include <algorithm>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "../host/qtorch.hpp"
+#include "../host/maxcut.h"
+
+static std::vector<double> nelderMeadMaximise(const std::function<double(const std::vector<double> &)> &f, std::vector<double> x0,
+                                              int maxEvals, double step, int &evals) {
+    const size_t n = x0.size();
+    std::vector<std::vector<double>> simplex(n + 1, x0);
+    for (size_t i = 0; i < n; ++i) simplex[i + 1][i] += step;
+    std::vector<double> val(n + 1);
+    evals = 0;
+    for (size_t i = 0; i <= n; ++i) { val[i] = f(simplex[i]); ++evals; }
+    auto combine = [&](const std::vector<double> &c, const std::vector<double> &w, double t) {
+        std::vector<double> r(n);
+        for (size_t i = 0; i < n; ++i) r[i] = c[i] + t * (c[i] - w[i]);
+        return r;
+    };
+    while (evals < maxEvals) {
+        std::vector<size_t> idx(n + 1);
+        for (size_t i = 0; i <= n; ++i) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return val[a] > val[b]; });      // best first (maximise)
+        const size_t best = idx[0], worst = idx[n], second = idx[n - 1];
+        if (std::abs(val[best] - val[worst]) < 1e-12) break;
+        std::vector<double> centroid(n, 0.0);
+        for (size_t i = 0; i < n; ++i) for (size_t d = 0; d < n; ++d) centroid[d] += simplex[idx[i]][d] / n;
+        std::vector<double> refl = combine(centroid, simplex[worst], 1.0);
+        const double fr = f(refl); ++evals;
+        if (fr > val[best]) {
+            std::vector<double> exp = combine(centroid, simplex[worst], 2.0);
+            const double fe = f(exp); ++evals;
+            if (fe > fr) { simplex[worst] = exp; val[worst] = fe; } else { simplex[worst] = refl; val[worst] = fr; }
+        } else if (fr > val[second]) {
+            simplex[worst] = refl; val[worst] = fr;
+        } else {
+            std::vector<double> con = combine(centroid, simplex[worst], -0.5);
+            const double fc = f(con); ++evals;
+            if (fc > val[worst]) { simplex[worst] = con; val[worst] = fc; }
+            else {
+                for (size_t i = 1; i <= n; ++i) {
+                    for (size_t d = 0; d < n; ++d) simplex[idx[i]][d] = simplex[best][d] + 0.5 * (simplex[idx[i]][d] - simplex[best][d]);
+                    val[idx[i]] = f(simplex[idx[i]]); ++evals;
+                }
+            }
+        }
+    }
+    size_t b = 0;
+    for (size_t i = 1; i <= n; ++i) if (val[i] > val[b]) b = i;
+    return simplex[b];
+}
+
+int main(int argc, char *argv[]) {
+    if (argc < 5) {
+        std::cout << "Not enough arguments" << std::endl;
+        std::cout << "arguments: <GraphFile Path> <p value> <0 for getAngles> <file path to output angle file> [max objective evaluations]\n";
+        return -1;
+    }
+    const int p = atoi(argv[2]), mode = atoi(argv[3]);
+    if (mode != 0) {
+        std::cout << "Only mode 0 (optimal angles) is provided by the B200 build; the final-string sampler is not." << std::endl;
+        return -1;
+    }
+    const std::string outputPath(argv[4]);
+    const int maxEvals = argc > 5 ? atoi(argv[5]) : 200;
+    mkdir("output", 0755);
+    try {
+        Timer clock;
+        clock.start();
+        ExtraData data(p, argv[1]);
+        data.outputFile = outputPath;
+        QaoaObjective objective(data);
+        std::cout << "Planned " << data.pairs.size() << " edge terms in " << clock.getElapsed() << " seconds; " << objective.UnitsPerEvaluation()
+                  << " units and " << objective.LaunchesPerEvaluation() << " kernel launch(es) per objective evaluation" << std::endl;
+        std::vector<double> start(2 * p);
+        for (int i = 0; i < p; ++i) { start[i] = 0.392699; start[i + p] = 0.785399; }
+        double bestSeen = -1.0;
+        auto F_p = [&](const std::vector<double> &bg) {
+            const double v = objective(bg);
+            std::ofstream angles(outputPath);
+            for (double a : bg) angles << a << " ";
+            bestSeen = std::max(bestSeen, v);
+            return v;
+        };
+        Timer opt;
+        opt.start();
+        int evals = 0;
+        const std::vector<double> best = nelderMeadMaximise(F_p, start, maxEvals, 0.1, evals);
+        const double seconds = opt.getElapsed();
+        {
+            std::ofstream angles(outputPath);
+            for (double a : best) angles << a << " ";
+        }
+        std::cout << "F_p(start) evaluations: " << evals << ", best F_p = " << bestSeen << std::endl;
+        std::cout << "Terms per second: " << evals * static_cast<double>(data.pairs.size()) / seconds << std::endl;
+        std::cout << "Took " << clock.getElapsed() << " seconds" << std::endl;
+    } catch (std::exception &e) {
+        std::cout << e.what() << std::endl;
+        return -1;
+    } catch (const char *msg) {
+        std::cout << msg << std::endl;
+        return -1;
+    }
+    return 0;
+}

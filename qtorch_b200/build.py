@@ -45,7 +45,7 @@ def build_host(force=False):
     os.makedirs(BIN, exist_ok=True)
     hdrs = _sources("host", (".h", ".hpp")) + [os.path.join(ROOT, "include", "qtorch_b200.h"), LIB]
     out = []
-    for name, src in (("qtb_harness", "qtb_harness.cpp"), ("qtorch", "qtorch_main.cpp")):
+    for name, src in (("qtb_harness", "qtb_harness.cpp"), ("qtorch", "qtorch_main.cpp"), ("maxcutQAOA", "maxcut_main.cpp")):
         target = os.path.join(BIN, name)
         source = os.path.join(HERE, "apps", src)
         if force or _newer(target, hdrs + [source]):

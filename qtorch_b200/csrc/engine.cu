@@ -316,6 +316,7 @@ struct qtb_ctx_s {
     bool trace = false;
     std::vector<TraceRec> traceRecs;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    double *batchOut = nullptr; size_t batchOutCap = 0;      // pinned gather buffer of qtb_plans_run_batched
     // NCCL
     void *comm = nullptr; int nRanks = 1, rank = 0;
     double *commBuf = nullptr; size_t commBufElems = 0;

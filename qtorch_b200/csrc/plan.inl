@@ -309,6 +309,45 @@ int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *pl, int slot) {
     CU(cudaMemcpyAsync(pl->inBlobDev, pl->slotDev[slot], pl->inBlobBytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return plan_run_locked(ctx, pl);
 }
+int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const double *const *const *hostInputs, double *hostOut) {
+    if (!ctx || !plans || n < 1 || !hostInputs || !hostOut) return fail(QTB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    ST(flush_locked(ctx));
+    bool allMicro = true;
+    for (int i = 0; i < n; i++) {
+        if (!plans[i] || plans[i]->outRank != 0) return fail(QTB_ERR_INVALID, "batched plans must have scalar outputs");
+        if (plans[i]->segs.size() != 1 || !plans[i]->segs[0].micro) allMicro = false;
+    }
+    for (int i = 0; i < n; i++) ST(plan_upload_locked(ctx, plans[i], hostInputs[i]));
+    if (allMicro) {
+        // one CTA per plan: absolute blob addresses through the staging ring
+        size_t off = 0;
+        ST(ring_reserve(ctx, (size_t)n * 8, off));
+        uint64_t *addr = reinterpret_cast<uint64_t *>(ctx->ringHost + off);
+        for (int i = 0; i < n; i++) addr[i] = reinterpret_cast<uint64_t>(plans[i]->microBlobDev);
+        CU(cudaMemcpyAsync(ctx->ringDev + off, ctx->ringHost + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_micro<<<n, QTB_MICRO_THREADS, 0, ctx->stream>>>(nullptr, reinterpret_cast<const uint64_t *>(ctx->ringDev + off));
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ringEvent, ctx->stream));
+        ctx->ringEventValid = true;
+        ctx->stats.launches++;
+        for (int i = 0; i < n; i++) { ctx->stats.steps += plans[i]->nSteps; ctx->stats.micro_steps += plans[i]->nMicroSteps; ctx->stats.units += plans[i]->units; }
+    } else {
+        for (int i = 0; i < n; i++) ST(plan_run_locked(ctx, plans[i]));
+    }
+    // gather the n scalars: n tiny async copies into pinned memory, one wait
+    if ((size_t)n > ctx->batchOutCap) {
+        if (ctx->batchOut) cudaFreeHost(ctx->batchOut);
+        ctx->batchOutCap = std::max<size_t>(256, (size_t)n * 2);
+        CU(cudaMallocHost((void **)&ctx->batchOut, ctx->batchOutCap * 16));
+    }
+    for (int i = 0; i < n; i++) CU(cudaMemcpyAsync(ctx->batchOut + 2 * i, plans[i]->outDev, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(hostOut, ctx->batchOut, (size_t)n * 16);
+    ctx->stats.bytes_d2h += (long long)n * 16;
+    return QTB_OK;
+}
 int qtb_plan_output_rank(qtb_plan *pl) { return pl ? pl->outRank : -1; }
 long long qtb_plan_units(qtb_plan *pl) { return pl ? pl->units : 0; }
 int qtb_plan_launches(qtb_plan *pl) { return pl ? pl->launches : 0; }

@@ -63,6 +63,13 @@ public:
         ParseNetwork(inputFile);
     }
 
+    // addition: build from in-memory text (same grammar as the files): the term dispatcher hands circuits over
+    // without the reference's write-file / re-parse round trip (maxcut.cpp:172-193)
+    Network(std::istream &qasmText, const std::string &measurementText) : mInputFile("<memory>"), mMeasureFile("<memory>") {
+        std::istringstream meas(measurementText);
+        ParseStreams(qasmText, meas, true);
+    }
+
     std::shared_ptr<Node> ContractNodes(std::shared_ptr<Node> nodeA, std::shared_ptr<Node> nodeB, int threshold);
 
     const std::complex<double> &GetFinalValue() const noexcept {
@@ -121,6 +128,7 @@ protected:
                                 std::shared_ptr<Node> nodeA, std::shared_ptr<Node> nodeB, std::shared_ptr<Node> nodeC);
     void ParseTokens(std::string &input, std::vector<std::string> &output);
     void ParseNetwork(const std::string &inputFile);
+    void ParseStreams(std::istream &input, std::istream &measureStream, bool measureOpen);
     void ParseNode(std::string &inputLine);
     void CreateInitialStates();
     void AddMeasurementsOrTrace(std::vector<char> &measurements);
@@ -192,13 +200,18 @@ inline void Network::AddMeasurementsOrTrace(std::vector<char> &measurements) {
 }
 
 inline void Network::ParseNetwork(const std::string &inputFile) {
-    mAllNodes.reserve(4096);
     std::ifstream input(inputFile);
     if (!input.is_open()) {
         std::cout << "Failed to open QASM file!" << std::endl;
         mFailure = true;
         throw InvalidFile();
     }
+    std::ifstream measureStream(mMeasureFile);
+    ParseStreams(input, measureStream, measureStream.is_open());
+}
+
+inline void Network::ParseStreams(std::istream &input, std::istream &measureStream, bool measureOpen) {
+    mAllNodes.reserve(4096);
     std::string line;
     std::getline(input, line);                 // first line: number of qubits
     mNumberOfQubits = std::stoi(line);
@@ -210,16 +223,13 @@ inline void Network::ParseNetwork(const std::string &inputFile) {
         std::getline(input, line);
         ParseNode(line);
     }
-    input.close();
 
     // measurement string: one character per qubit, whitespace ignored, missing entries trace the qubit out
     std::vector<char> measurements(mNumberOfQubits);
-    std::ifstream measureStream(mMeasureFile);
-    if (!measureStream.is_open())
-        std::cout << "Measurement file failed to open - all qubits will be traced out" << std::endl;
+    if (!measureOpen) std::cout << "Measurement file failed to open - all qubits will be traced out" << std::endl;
     for (int q = 0; q < mNumberOfQubits; ++q) {
         char c;
-        measurements[q] = (measureStream >> c) ? c : 'T';
+        measurements[q] = (measureOpen && (measureStream >> c)) ? c : 'T';
     }
     AddMeasurementsOrTrace(measurements);
 

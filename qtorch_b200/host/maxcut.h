@@ -1,0 +1,298 @@
+// qtorch_b200/host/maxcut.h -- QAOA MaxCut helpers (counterpart of /root/reference/src/maxcut.h:31-233) and the
+// B200 term dispatcher that replaces the serial per-edge loop of F_p (/root/reference/src/maxcut.cpp:162-204).
+//
+// Kept from the reference (same names, same results): ExtraData (graph reader + per-edge light-cone extraction with
+// its qubit-relabelling order), outputInitialPlusStateToFile, applyU_CsThenU_Bs (now writing to any std::ostream).
+// New: QaoaObjective -- every edge's light-cone circuit is built IN MEMORY (no input/tempMaxCut.qasm round trip;
+// angles still pass through the 6-significant-digit text form and std::stof, so tensors are bit-identical to what
+// the reference parses back), planned once (plan topology does not depend on the angles), compiled to a device
+// plan, and all edges owned by this rank are evaluated in one grouped launch per objective evaluation
+// (qtb_plans_run_batched).  Edges are dealt round-robin over ranks; the partial sums meet in one allreduce.
+#pragma once
+
+#include <fstream>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "ContractionTools.h"
+#include "preprocess.h"
+
+namespace qtorch {
+
+struct ExtraData {
+    ExtraData(const int p0, const char *filename0) : fileName(filename0), p(p0) { ReadInData(); PopulateIterations(); }
+    ExtraData() {}
+    std::string fileName;
+    std::vector<std::pair<int, int>> pairs;                      // graph edges in file order
+    std::vector<std::vector<int>> adjacencyLists;
+    std::vector<int> qubitsNeeded;                               // light-cone size per edge
+    std::string outputFile;
+    int numQubits{0};
+    int p{1};
+    std::vector<std::vector<std::pair<int, int>>> iterations;     // light-cone edges per term, graph vertex ids
+    std::vector<std::vector<std::pair<int, int>>> realIterations; // the same in the term's own qubit numbering
+
+    // ".dgf": "c ..." comment lines, "e u v" edges; vertex count = largest id + 1 (reference maxcut.h:56-103)
+    void ReadInData() {
+        std::ifstream input(fileName);
+        if (!input.is_open()) {
+            std::cout << "Could Not Open File" << std::endl;
+            throw "File Not Open";
+        }
+        int largest = 0;
+        char tag;
+        std::string rest;
+        while (input >> tag) {
+            if (tag != 'e') {
+                if (tag != 'c') std::cout << "Error parsing file" << std::endl;
+                std::getline(input, rest);
+                continue;
+            }
+            int u, v;
+            input >> u >> v;
+            largest = std::max(largest, std::max(u, v));
+            pairs.push_back({u, v});
+        }
+        numQubits = largest + 1;
+        adjacencyLists.assign(numQubits, std::vector<int>());
+        for (const auto &e : pairs) {
+            adjacencyLists[e.first].push_back(e.second);
+            adjacencyLists[e.second].push_back(e.first);
+        }
+    }
+
+    // For every edge: breadth-first growth of the light cone, p rounds.  Term-local qubit ids are handed out in
+    // order of first appearance while scanning adjacency lists -- so qubit 1 is the FIRST LISTED NEIGHBOUR of the
+    // edge's first vertex, not necessarily its partner (reference quirk, maxcut.h:105-185).
+    void PopulateIterations() {
+        const size_t nTerms = pairs.size();
+        qubitsNeeded.assign(nTerms, 0);
+        iterations.assign(nTerms, std::vector<std::pair<int, int>>());
+        realIterations.assign(nTerms, std::vector<std::pair<int, int>>());
+        std::vector<int> localId(numQubits);
+        for (size_t term = 0; term < nTerms; ++term) {
+            std::fill(localId.begin(), localId.end(), -1);
+            std::vector<int> frontier{pairs[term].first, pairs[term].second};
+            localId[pairs[term].first] = 0;
+            qubitsNeeded[term] = 1;
+            std::vector<bool> next(numQubits, false), done(numQubits, false), inFrontier(numQubits, false);
+            inFrontier[pairs[term].first] = inFrontier[pairs[term].second] = true;
+            PopulateIterationsHelper(0, frontier, next, done, inFrontier, static_cast<int>(term), localId);
+            for (const auto &e : iterations[term]) realIterations[term].push_back({localId[e.first], localId[e.second]});
+        }
+    }
+
+    void PopulateIterationsHelper(int counter, std::vector<int> &workingVerticesList, std::vector<bool> &newWorkingVertices,
+                                  std::vector<bool> &hasBeenChecked, std::vector<bool> &isInWorkingNodes, int iterationIndex,
+                                  std::vector<int> &mapToRealIt) {
+        for (int round = counter; round < p; ++round) {
+            for (int v : workingVerticesList) {
+                for (int nb : adjacencyLists[v]) {
+                    if (hasBeenChecked[nb]) continue;
+                    if (mapToRealIt[nb] == -1) mapToRealIt[nb] = qubitsNeeded[iterationIndex]++;
+                    iterations[iterationIndex].push_back({v, nb});
+                    if (!isInWorkingNodes[nb]) newWorkingVertices[nb] = true;
+                }
+                hasBeenChecked[v] = true;
+            }
+            workingVerticesList.clear();
+            std::fill(isInWorkingNodes.begin(), isInWorkingNodes.end(), false);
+            for (int v = 0; v < static_cast<int>(newWorkingVertices.size()); ++v) {
+                if (newWorkingVertices[v]) {
+                    workingVerticesList.push_back(v);
+                    isInWorkingNodes[v] = true;
+                }
+            }
+            std::fill(newWorkingVertices.begin(), newWorkingVertices.end(), false);
+        }
+    }
+};
+
+// |+>^n
+inline void outputInitialPlusStateToFile(std::ostream &qasm, const int numQubits) {
+    for (int q = 0; q < numQubits; ++q) qasm << "H " << q << std::endl;
+}
+
+// p layers of  [ CNOT a b ; Rz(-gamma) b ; CNOT a b  per light-cone edge ]  then  Rx(2 beta) on every qubit.
+// betas_gammas = (beta_1..beta_p, gamma_1..gamma_p); default stream precision (6 significant digits), as the reference.
+inline void applyU_CsThenU_Bs(const std::vector<std::pair<int, int>> &objectiveF, const int p, const std::vector<double> &betas_gammas,
+                              const int numQubits, std::ostream &output) {
+    for (int layer = 0; layer < p; ++layer) {
+        const double gamma = betas_gammas[layer + p], beta = betas_gammas[layer];
+        for (const auto &e : objectiveF) {
+            output << "CNOT " << e.first << " " << e.second << std::endl;
+            output << "Rz " << -gamma << " " << e.second << std::endl;
+            output << "CNOT " << e.first << " " << e.second << std::endl;
+        }
+        for (int q = 0; q < numQubits; ++q) output << "Rx " << beta * 2.0 << " " << q << std::endl;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// The B200 term dispatcher
+class QaoaObjective {
+public:
+    // rank/world: which share of the edges this process owns (edge e belongs to rank e % world).
+    // allreduce: sums an array of n doubles in place over all ranks (nullptr for a single rank).
+    QaoaObjective(const ExtraData &data, int rank = 0, int world = 1, std::function<void(double *, int)> allreduce = nullptr,
+                  int planTries = 8)
+        : mData(data), mRank(rank), mWorld(world), mAllReduce(allreduce) {
+        for (size_t e = static_cast<size_t>(rank); e < mData.pairs.size(); e += static_cast<size_t>(world)) mOwned.push_back(static_cast<int>(e));
+        std::vector<double> bg(2 * mData.p);
+        for (int i = 0; i < mData.p; ++i) { bg[i] = 0.392699; bg[i + mData.p] = 0.785399; }      // maxcut.cpp:155-157
+        for (int e : mOwned) mTerms.push_back(BuildTerm(e, bg, planTries));
+    }
+    ~QaoaObjective() {
+        if (device::Engine::Get().alive())
+            for (auto &t : mTerms) if (t.plan) qtb_plan_destroy(device::Engine::Get().ctx(), t.plan);
+    }
+    QaoaObjective(const QaoaObjective &) = delete;
+    QaoaObjective &operator=(const QaoaObjective &) = delete;
+
+    // circuit text of one edge's light cone for the given angles (what the reference writes to input/tempMaxCut.qasm)
+    std::string CircuitText(int edge, const std::vector<double> &betas_gammas) const {
+        std::ostringstream q;
+        const int nq = mData.qubitsNeeded[edge];
+        q << nq << std::endl;
+        outputInitialPlusStateToFile(q, nq);
+        applyU_CsThenU_Bs(mData.realIterations[edge], mData.p, betas_gammas, nq, q);
+        return q.str();
+    }
+    static std::string MeasurementText(int numQubits) {
+        std::string m;
+        for (int i = 0; i < numQubits; ++i) m += (i < 2) ? "Z " : "T ";
+        return m;
+    }
+
+    // <Z Z> of every edge owned by this rank, one grouped launch
+    std::vector<std::complex<double>> EvaluateOwnedTerms(const std::vector<double> &betas_gammas) {
+        std::vector<qtb_plan *> plans;
+        std::vector<const double *const *> inputPtrs;
+        for (auto &t : mTerms) {
+            RefreshAngles(t, betas_gammas);
+            plans.push_back(t.plan);
+            inputPtrs.push_back(t.ptrs.data());
+        }
+        std::vector<double> out(2 * mTerms.size());
+        if (!mTerms.empty())
+            device::check(qtb_plans_run_batched(device::Engine::Get().ctx(), plans.data(), static_cast<int>(plans.size()), inputPtrs.data(), out.data()));
+        std::vector<std::complex<double>> vals(mTerms.size());
+        for (size_t i = 0; i < mTerms.size(); ++i) vals[i] = {out[2 * i], out[2 * i + 1]};
+        return vals;
+    }
+
+    // F_p = sum_edges 1/2 (1 - Re<Z Z>)   (maxcut.cpp:196), summed over ranks
+    double operator()(const std::vector<double> &betas_gammas) {
+        double partial = 0.0;
+        for (const auto &v : EvaluateOwnedTerms(betas_gammas)) partial += 0.5 * (1.0 - v.real());
+        if (mAllReduce && mWorld > 1) {
+            double buf[2] = {partial, 0.0};
+            mAllReduce(buf, 1);
+            partial = buf[0];
+        }
+        ++mEvaluations;
+        return partial;
+    }
+
+    const std::vector<int> &OwnedEdges() const { return mOwned; }
+    long long Evaluations() const { return mEvaluations; }
+    long long UnitsPerEvaluation() const { long long u = 0; for (const auto &t : mTerms) u += t.units; return u; }
+    int LaunchesPerEvaluation() const { int n = 0; bool allMicro = true; for (const auto &t : mTerms) { n += qtb_plan_launches(t.plan); if (qtb_plan_launches(t.plan) != 1) allMicro = false; } return allMicro ? 1 : n; }
+
+private:
+    struct AngleSlot { int input; bool isRx; int layer; };     // which plan input is Rz(-gamma_layer) / Rx(2 beta_layer)
+    struct Term {
+        int edge{0};
+        qtb_plan *plan{nullptr};
+        long long units{0};
+        std::vector<std::vector<std::complex<double>>> inputs;   // host tensors of all original nodes, id order
+        std::vector<const double *> ptrs;
+        std::vector<AngleSlot> slots;
+    };
+
+    // the value the reference's parser would obtain: default-precision text, then std::stof (Network.h:342,402)
+    static double ThroughText(double angle) {
+        std::ostringstream os;
+        os << angle;
+        return static_cast<double>(std::stof(os.str()));
+    }
+
+    Term BuildTerm(int edge, const std::vector<double> &bg, int planTries) {
+        Term t;
+        t.edge = edge;
+        const int nq = mData.qubitsNeeded[edge];
+        const std::string text = CircuitText(edge, bg), meas = MeasurementText(nq);
+        // plan search on the host only (plan-only mode records steps without arithmetic): best of a few seeded
+        // stochastic searches, cheapest by the reference's own unit count
+        const bool before = device::Engine::PlanOnly();
+        device::Engine::SetPlanOnly(true);
+        std::shared_ptr<Network> best;
+        for (int attempt = 0; attempt < planTries; ++attempt) {
+            std::istringstream qs(text);
+            std::shared_ptr<Network> net = std::make_shared<Network>(qs, meas);
+            if (attempt == 0) SnapshotInputs(*net, t);
+            ContractionTools tools(net);
+            tools.SetSeed(1000003u * static_cast<unsigned>(edge) + static_cast<unsigned>(attempt));
+            tools.Contract(Stochastic);
+            if (!best || net->getNumFloatOps() < best->getNumFloatOps()) best = net;
+        }
+        device::Engine::SetPlanOnly(before);
+        t.units = best->getNumFloatOps();
+        std::vector<qtb_plan_step> steps;
+        for (const auto &r : best->GetPlan()) {
+            qtb_plan_step s;
+            std::memset(&s, 0, sizeof(s));
+            s.a = r.a; s.b = r.b; s.k = static_cast<int>(r.posA.size());
+            for (int j = 0; j < s.k; ++j) { s.pos_a[j] = static_cast<int8_t>(r.posA[j]); s.pos_b[j] = static_cast<int8_t>(r.posB[j]); }
+            steps.push_back(s);
+        }
+        std::vector<int> ranks;
+        for (const auto &in : t.inputs) { int r = 0; while ((static_cast<size_t>(1) << (2 * r)) < in.size()) ++r; ranks.push_back(r); }
+        device::check(qtb_plan_create(device::Engine::Get().ctx(), static_cast<int>(ranks.size()), ranks.data(), static_cast<int>(steps.size()),
+                                      steps.data(), &t.plan));
+        for (const auto &in : t.inputs) t.ptrs.push_back(reinterpret_cast<const double *>(in.data()));
+        return t;
+    }
+
+    // copy every original node's tensor; remember which ones carry an angle (file order: per layer, per light-cone
+    // edge one Rz, then one Rx per qubit)
+    void SnapshotInputs(Network &net, Term &t) {
+        const int n = net.GetNumOriginalNodes();
+        std::vector<int> rzSeen(mData.p, 0), rxSeen(mData.p, 0);
+        const int rzPerLayer = static_cast<int>(mData.realIterations[t.edge].size()), rxPerLayer = mData.qubitsNeeded[t.edge];
+        int rzCount = 0, rxCount = 0;
+        for (int i = 0; i < n; ++i) {
+            const std::shared_ptr<Node> &node = net.GetAllNodes()[i];
+            t.inputs.push_back(node->GetTensorVals());
+            if (node->GetTypeOfNode() == GateType::RZ) t.slots.push_back({i, false, rzCount++ / rzPerLayer});
+            else if (node->GetTypeOfNode() == GateType::RX) t.slots.push_back({i, true, rxCount++ / rxPerLayer});
+        }
+        (void)rzSeen; (void)rxSeen;
+    }
+
+    void RefreshAngles(Term &t, const std::vector<double> &bg) {
+        for (const auto &s : t.slots) {
+            if (s.isRx) {
+                RxNode g(ThroughText(bg[s.layer] * 2.0));
+                t.inputs[s.input] = g.GetTensorVals();
+            } else {
+                RzNode g(ThroughText(-bg[s.layer + mData.p]));
+                t.inputs[s.input] = g.GetTensorVals();
+            }
+            t.ptrs[s.input] = reinterpret_cast<const double *>(t.inputs[s.input].data());
+        }
+    }
+
+    ExtraData mData;
+    int mRank, mWorld;
+    std::function<void(double *, int)> mAllReduce;
+    std::vector<int> mOwned;
+    std::vector<Term> mTerms;
+    long long mEvaluations{0};
+};
+
+}  // namespace qtorch

@@ -37,8 +37,71 @@ def host_library():
         H.qth_contract_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, cd, cll, ci, cd]
         H.qth_contract_sequence.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ctypes.c_int, cd, cll, ci, cd]
         H.qth_export_plan_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_QthPlan)]
+        H.qth_maxcut_circuit_text.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, cd, ctypes.c_char_p, ctypes.c_int, ci, ci]
+        H.qth_qaoa_create.restype = ctypes.c_void_p
+        H.qth_qaoa_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        H.qth_qaoa_destroy.argtypes = [ctypes.c_void_p]
+        H.qth_qaoa_num_owned.argtypes = [ctypes.c_void_p]
+        H.qth_qaoa_owned_edges.argtypes = [ctypes.c_void_p, ci]
+        H.qth_qaoa_units.restype = ctypes.c_longlong
+        H.qth_qaoa_units.argtypes = [ctypes.c_void_p]
+        H.qth_qaoa_launches.argtypes = [ctypes.c_void_p]
+        H.qth_qaoa_evaluate.argtypes = [ctypes.c_void_p, cd, ctypes.c_int, cd, cd]
+        H.qth_qaoa_circuit_text.argtypes = [ctypes.c_void_p, ctypes.c_int, cd, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
         _hlib = H
     return _hlib
+
+
+def maxcut_circuit_text(graph_file, p, edge, betas_gammas):
+    """host-only: (circuit text, number of edges, qubits of this term) exactly as the reference's F_p writes it"""
+    H = host_library()
+    bg = (ctypes.c_double * len(betas_gammas))(*betas_gammas)
+    buf = ctypes.create_string_buffer(1 << 16)
+    ne, nq = ctypes.c_int(), ctypes.c_int()
+    n = H.qth_maxcut_circuit_text(graph_file.encode(), p, edge, bg, buf, len(buf), ctypes.byref(ne), ctypes.byref(nq))
+    if n < 0:
+        _raise(H, n)
+    return buf.value.decode(), ne.value, nq.value
+
+
+class QaoaObjective:
+    """The B200 term dispatcher of host/maxcut.h: per-edge light-cone networks of a MaxCut QAOA instance, planned once,
+    evaluated in one grouped launch per call.  rank/world select this process's share of the edges (edge % world)."""
+
+    def __init__(self, graph_file, p=1, rank=0, world=1, plan_tries=8):
+        self.H = host_library()
+        self.p = p
+        self.h = self.H.qth_qaoa_create(graph_file.encode(), p, rank, world, plan_tries)
+        if not self.h:
+            _raise(self.H, 1)
+        n = self.H.qth_qaoa_num_owned(self.h)
+        buf = (ctypes.c_int * max(n, 1))()
+        self.H.qth_qaoa_owned_edges(self.h, buf)
+        self.owned = [buf[i] for i in range(n)]
+        self.units = self.H.qth_qaoa_units(self.h)
+        self.launches = self.H.qth_qaoa_launches(self.h)
+
+    def evaluate(self, betas_gammas):
+        """-> (array of <ZZ> for the owned edges, this rank's partial F_p)"""
+        bg = (ctypes.c_double * len(betas_gammas))(*betas_gammas)
+        out = (ctypes.c_double * max(2 * len(self.owned), 2))()
+        fp = ctypes.c_double()
+        rc = self.H.qth_qaoa_evaluate(self.h, bg, len(betas_gammas), out, ctypes.byref(fp))
+        if rc != 0:
+            _raise(self.H, rc)
+        vals = np.array([complex(out[2 * i], out[2 * i + 1]) for i in range(len(self.owned))])
+        return vals, fp.value
+
+    def circuit_text(self, edge, betas_gammas):
+        bg = (ctypes.c_double * len(betas_gammas))(*betas_gammas)
+        buf = ctypes.create_string_buffer(1 << 16)
+        self.H.qth_qaoa_circuit_text(self.h, edge, bg, len(betas_gammas), buf, len(buf))
+        return buf.value.decode()
+
+    def close(self):
+        if self.h:
+            self.H.qth_qaoa_destroy(self.h)
+            self.h = None
 
 
 def _raise(H, rc):
