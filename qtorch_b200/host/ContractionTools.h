@@ -169,7 +169,7 @@ inline std::shared_ptr<Network> ContractionTools::ParallelContract(std::mt19937 
         int threshold = -1, fails = 0;
         while (!net->IsDone()) {
             if (fails > std::pow(left.size(), 2)) {
-                std::cout << "Nodes left: " << left.size() << std::endl;
+                if (!detail::quietMode()) std::cout << "Nodes left: " << left.size() << std::endl;
                 ++threshold;
                 fails = 0;
             }

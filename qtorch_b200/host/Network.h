@@ -538,8 +538,13 @@ inline void Network::ReduceCircuit() {
                 fused->SetTypeOfNode(GateType::INITSTATE);
                 fused->SetTypeOfNodeString("INITSTATE(Manipulated)");
             }
-            FindAndReplace(mNodesByWire, before, fused);
-            FindAndReplace(kept, before, fused);
+            // `before` only ever sits on its own qubit lines, so searching those is equivalent to the reference's
+            // scan over every line (Network.h:1034-1035) at O(1) instead of O(#qubits) per merge
+            for (int line : before->GetWireNumber()) {
+                if (line < 0 || line >= mNumberOfQubits) continue;
+                FindAndReplace(mNodesByWire[line], before, fused);
+                FindAndReplace(kept[line], before, fused);
+            }
         }
     }
     mNodesByWire = std::move(kept);
@@ -550,20 +555,23 @@ inline void Network::ReduceCircuit() {
     std::vector<int> cursor(nq, 0);
     std::vector<bool> advanced(nq, false);
     bool fusedThisSweep = false;
+    std::vector<int> active(nq);                        // lines that still have nodes to place, ascending
+    for (int q = 0; q < nq; ++q) active[q] = q;
     for (;;) {
-        for (int q = 0; q < nq; ++q) {
+        for (int q : active) {
             if (cursor[q] >= static_cast<int>(mNodesByWire[q].size()) || advanced[q]) continue;
-            std::shared_ptr<Node> cand = mNodesByWire[q][cursor[q]];
-            if (cand->mRank == 1) {
-                head[q] = cand;
+            Node *peek = mNodesByWire[q][cursor[q]].get();       // no shared_ptr copy in this (hot) scan
+            if (peek->mRank == 1) {
+                head[q] = mNodesByWire[q][cursor[q]];
                 advanced[q] = true;
                 ++cursor[q];
                 continue;
             }
-            const int qa = cand->GetWireNumber()[0], qb = cand->GetWireNumber()[1];
+            const int qa = peek->GetWireNumber()[0], qb = peek->GetWireNumber()[1];
             if (advanced[qb] || advanced[qa]) continue;
             // the gate must be next on BOTH of its lines
-            if (mNodesByWire[qa][cursor[qa]] != mNodesByWire[qb][cursor[qb]]) continue;
+            if (mNodesByWire[qa][cursor[qa]].get() != mNodesByWire[qb][cursor[qb]].get()) continue;
+            std::shared_ptr<Node> cand = mNodesByWire[q][cursor[q]];
             if (head[qa] == head[qb]) {
                 // previous node on both lines is one and the same two-qubit node: fuse (later gate is operand A)
                 head[qa] = ContractNodes(cand, head[qa], 0);
@@ -579,18 +587,23 @@ inline void Network::ReduceCircuit() {
             advanced[qa] = advanced[qb] = true;
         }
         bool any = false;
-        for (int q = 0; q < nq; ++q) {
+        for (int q : active) {
             if (advanced[q]) {
                 any = true;
                 if (fusedThisSweep && !merged[q].empty()) merged[q].back() = head[q];
                 else merged[q].push_back(head[q]);
-            } else if (cursor[q] < static_cast<int>(mNodesByWire[q].size()) && !fusedThisSweep) {
-                merged[q].push_back(nullptr);
+                advanced[q] = false;
             }
+            // The reference pads waiting lines with a nullptr per sweep (Network.h:1102-1104).  Every reader of
+            // mNodesByWire skips nullptr entries (Network.h:1179,1217), so the padding is unobservable; it is left
+            // out because it costs O(depth x qubits) memory and time (16 MB for the 1000-qubit GHZ chain).
         }
-        std::fill(advanced.begin(), advanced.end(), false);
         fusedThisSweep = false;
         if (!any) break;
+        // finished lines can never advance again: drop them (they were skipped by the first test anyway)
+        size_t keep = 0;
+        for (int q : active) if (cursor[q] < static_cast<int>(mNodesByWire[q].size())) active[keep++] = q;
+        active.resize(keep);
     }
     mNodesByWire = std::move(merged);
 }

@@ -180,6 +180,13 @@ protected:
     GateType mType{GateType::INTERMEDIATESTATE};
     std::string mStringType{"INTERMEDIATESTATE"};
 
+    // constant gates are built once per process and copied afterwards (a circuit has thousands of CNOT / H nodes)
+    template <class Builder>
+    void fillCached(std::vector<cplx> &cache, Builder build) {
+        if (cache.empty()) { build(); cache = GetTensorVals(); }
+        else GetTensorVals() = cache;
+    }
+
     // ---- superoperator builders -----------------------------------------------------------------------
     // wire digit d <-> density-matrix element |row><col| with d = 2*row + col
     static int rowOf(int d) { return d >> 1; }
@@ -226,8 +233,8 @@ protected:
 class HNode : public Node {
 public:
     HNode() : Node(2) {
-        const cplx U[4] = {1.0, 1.0, 1.0, -1.0};
-        fillFromUnitary1(U, 0.5);                      // (1/sqrt2)^2 applied once, exactly
+        static std::vector<cplx> cache;
+        fillCached(cache, [this] { const cplx U[4] = {1.0, 1.0, 1.0, -1.0}; fillFromUnitary1(U, 0.5); });   // (1/sqrt2)^2 applied once, exactly
         mType = GateType::HADAMARD; mStringType = "H";
     }
 };
@@ -339,9 +346,12 @@ public:
 class CNOTNode : public Node {
 public:
     CNOTNode() : Node(4) {
-        cplx U[16] = {};
-        U[4 * 0 + 0] = 1; U[4 * 1 + 1] = 1; U[4 * 3 + 2] = 1; U[4 * 2 + 3] = 1;
-        fillFromUnitary2(U);
+        static std::vector<cplx> cache;
+        fillCached(cache, [this] {
+            cplx U[16] = {};
+            U[4 * 0 + 0] = 1; U[4 * 1 + 1] = 1; U[4 * 3 + 2] = 1; U[4 * 2 + 3] = 1;
+            fillFromUnitary2(U);
+        });
         mType = GateType::CNOT; mStringType = "CNOT";
     }
 };
