@@ -111,3 +111,30 @@ def test_config2_trace_is_one_full_size(built, tmp_path):
     val = complex(float(out["value"][0]), float(out["value"][1]))
     assert abs(val - 1.0) <= 1e-10, val
     assert out["plan"] == rec["plan"]
+
+
+def test_reference_test_suite_drop_in(built, tmp_path):
+    """the reference's own src/tests.cpp (13 known-answer tests: rotations, Bell/cat/teleportation/
+    Toffoli, arbitrary 1- and 2-qubit gates vs its in-test state-vector simulator, large QAOA circuits, random circuits,
+    disconnected networks, user-defined sequences, line graph + QuickBB), compiled UNMODIFIED against the B200 host
+    mirror (oracle/_ref/tests_dropin, built where /root/reference exists), must pass 13/13 on the GPU."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "tests_dropin")
+    qbb = os.path.join(ROOT, "oracle", "_ref", "quickbb_64")
+    if not (os.path.exists(exe) and os.path.exists(qbb)):
+        pytest.skip("oracle/_ref/tests_dropin not built (needs /root/reference at build time)")
+    work = os.path.join(str(tmp_path), "run")
+    os.makedirs(work)
+    shutil.copytree(os.path.join(GOLDEN, "Samples"), os.path.join(work, "Samples"))
+    os.makedirs(os.path.join(work, "output"))
+    env = dict(os.environ)
+    env["PATH"] = os.path.dirname(qbb) + ":" + env["PATH"]
+    env["QTORCH_QUIET"] = "1"
+    p = subprocess.run([exe], cwd=work, capture_output=True, text=True, timeout=1500, env=env)
+    log = open(os.path.join(work, "output", "testingoutput.log")).read()
+    lines = log.splitlines()
+    assert "TOTAL TEST FAILURE COUNT: 0." in log, log[-3000:]
+    assert sum(1 for l in lines if l.strip() == "Passed") == 13 and not any(l.strip() == "Failed" for l in lines), log[-3000:]
+    assert p.returncode == 0, p.stdout[-2000:]
