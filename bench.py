@@ -273,8 +273,15 @@ def main():
             avg_ms = sum(r["ms"] for r in gett) / len(gett)
             flop = 8.0 * 4 ** 17                                   # 8 * 4^(rC+k), rC = 14, k = 3
             ach = flop / (avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "k_gett<4,4,4,2,16,4> (warp-specialised FP64 DMMA tiles 128x64x16, the four rank-14 steps)", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
-                    "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "traffic": None, "launches_timed": len(gett), "avg_ms": avg_ms,
+            variant = os.environ.get("QTB_GETT_C1", "2")
+            three_m = variant in ("2", "3")
+            roof = {"bound": "tensor", "kernel": "k_gett (warp-specialised FP64 DMMA tiles, the four rank-14 steps), variant %s (%s complex product)" % (variant, "3M" if three_m else "4M"),
+                    "achieved": ach, "peak": FP64_PEAK_TFLOPS,
+                    "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
+                    # achieved counts the ALGORITHMIC 8 flops per complex MAC; the 3M kernel issues 6 on the tensor pipe
+                    "tensor_pipe_flops_per_unit": 6 if three_m else 8, "tensor_pipe_frac": ach * (0.75 if three_m else 1.0) / FP64_PEAK_TFLOPS,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_summary.txt); algorithmic 4.33e9
+                    "traffic": 4.50e9, "launches_timed": len(gett), "avg_ms": avg_ms,
                     "share_of_step": sum(r["ms"] for r in gett) / total_ms,
                     "peak_source": "measured: tools/probe_fp64 DMMA m8n8k4 on this pool's B200 (profiles/r01_probe_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry"}
         by_kind = {}

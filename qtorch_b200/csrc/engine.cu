@@ -48,19 +48,24 @@ struct GettChoice { int cfg; bool swap; };      // cfg: 0 C1/TK16 1 C1/TK4 2 C2/
 typedef void (*GettKernel)(const GettParams);
 struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; };
 // C1: 128x64 tile, compute-bound big x big;  C2: 256x16;  C3: 256x8 (N <= 4 padded) -- streaming
-static GettInst g_gett[7] = {
-    {k_gett<4, 2, 4, 4, 16, 4>, 128, 64, 16, GettCfg<4, 2, 4, 4, 16, 4>::NT, GettCfg<4, 2, 4, 4, 16, 4>::SMEM, 1},
+static GettInst g_gett[9] = {
+    {k_gett<4, 2, 4, 4, 16, 3>, 128, 64, 16, GettCfg<4, 2, 4, 4, 16, 3>::NT, GettCfg<4, 2, 4, 4, 16, 3>::SMEM, 1},
     {k_gett<4, 2, 4, 4, 4, 12>, 128, 64, 4, GettCfg<4, 2, 4, 4, 4, 12>::NT, GettCfg<4, 2, 4, 4, 4, 12>::SMEM, 1},
-    {k_gett<8, 1, 4, 2, 16, 3>, 256, 16, 16, GettCfg<8, 1, 4, 2, 16, 3>::NT, GettCfg<8, 1, 4, 2, 16, 3>::SMEM, 1},
+    {k_gett<8, 1, 4, 2, 16, 2>, 256, 16, 16, GettCfg<8, 1, 4, 2, 16, 2>::NT, GettCfg<8, 1, 4, 2, 16, 2>::SMEM, 1},
     {k_gett<8, 1, 4, 2, 4, 10>, 256, 16, 4, GettCfg<8, 1, 4, 2, 4, 10>::NT, GettCfg<8, 1, 4, 2, 4, 10>::SMEM, 1},
-    {k_gett<8, 1, 4, 1, 16, 3>, 256, 8, 16, GettCfg<8, 1, 4, 1, 16, 3>::NT, GettCfg<8, 1, 4, 1, 16, 3>::SMEM, 1},
+    {k_gett<8, 1, 4, 1, 16, 2>, 256, 8, 16, GettCfg<8, 1, 4, 1, 16, 2>::NT, GettCfg<8, 1, 4, 1, 16, 2>::SMEM, 1},
     {k_gett<8, 1, 4, 1, 4, 10>, 256, 8, 4, GettCfg<8, 1, 4, 1, 4, 10>::NT, GettCfg<8, 1, 4, 1, 4, 10>::SMEM, 1},
     // C1 with 16 math warps of 32x16
-    {k_gett<4, 4, 4, 2, 16, 4>, 128, 64, 16, GettCfg<4, 4, 4, 2, 16, 4>::NT, GettCfg<4, 4, 4, 2, 16, 4>::SMEM, 1},
+    {k_gett<4, 4, 4, 2, 16, 3>, 128, 64, 16, GettCfg<4, 4, 4, 2, 16, 3>::NT, GettCfg<4, 4, 4, 2, 16, 3>::SMEM, 1},
+    // C1 "3M": 64x64 tile, 16 math warps of 16x16, three real DMMAs per complex tile product
+    {k_gett<4, 4, 2, 2, 16, 5, 1>, 64, 64, 16, GettCfg<4, 4, 2, 2, 16, 5, 1>::NT, GettCfg<4, 4, 2, 2, 16, 5, 1>::SMEM, 1},
+    // C1 "3M", 8 math warps of 32x16 (more registers per warp: double-buffered fragments)
+    {k_gett<2, 4, 4, 2, 16, 5, 1>, 64, 64, 16, GettCfg<2, 4, 4, 2, 16, 5, 1>::NT, GettCfg<2, 4, 4, 2, 16, 5, 1>::SMEM, 1},
 };
 static int c1_variant() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("QTB_GETT_C1"); v = e ? atoi(e) : 1; }       // 1 = 16 math warps (default), 0 = 8
+    // 2 = "3M" complex product, 16 math warps (default);  3 = 3M, 8 math warps;  1 = 4M, 16 math warps;  0 = 4M, 8 math warps
+    if (v < 0) { const char *e = getenv("QTB_GETT_C1"); v = e ? atoi(e) : 2; }
     return v;
 }
 
@@ -119,7 +124,7 @@ static int choose_kind(const StepGeom &g, GettChoice &gc) {
     if (!force_generic() && bigFree >= 4 && g.k >= 1) {
         gc.swap = g.nfb > g.nfa;
         const int tk4 = (g.k == 1) ? 1 : 0;
-        if (smallFree >= 3) gc.cfg = (tk4 == 0 && c1_variant() == 1) ? 6 : 0 + tk4;
+        if (smallFree >= 3) gc.cfg = (tk4 == 0 && c1_variant() == 3) ? 8 : (tk4 == 0 && c1_variant() == 2) ? 7 : (tk4 == 0 && c1_variant() == 1) ? 6 : 0 + tk4;
         else if (smallFree == 2) gc.cfg = 2 + tk4;
         else gc.cfg = 4 + tk4;
         return KIND_GETT;
@@ -163,6 +168,11 @@ static void build_gett(const StepGeom &g, const GettChoice &gc, const double2 *A
     for (int j = 0; j < TKB; j++) v.push_back({p.shYk[j], TNB + j});
     std::sort(v.begin(), v.end(), [](const CB &a, const CB &b) { return a.shift < b.shift; });
     for (size_t j = 0; j < v.size(); j++) p.permY[j] = v[j].coord;
+    // shared-memory layouts: contiguous-in-HBM dimension contiguous in shared memory (see GettParams)
+    const int LDK = (inst.TK % 8 == 0) ? inst.TK + 4 : inst.TK;
+    const bool xKFast = p.permX[0] >= TMB, yKFast = (p.nyBits + TKB > 0) && p.permY[0] >= TNB;
+    if (xKFast) { p.xsX = (uint16_t)LDK; p.xsK = 1; } else { p.xsX = 1; p.xsK = (uint16_t)(inst.TM + 2); }
+    if (yKFast) { p.ysY = (uint16_t)LDK; p.ysK = 1; } else { p.ysY = 1; p.ysK = (uint16_t)(inst.TN + 2); }
 }
 
 static void build_reduce(const StepGeom &g, const double2 *A, const double2 *B, double2 *C, double2 *partial, ReduceParams &p) {

@@ -37,6 +37,11 @@ struct GettParams {
     uint8_t shXk[32], shYk[32];       // k bit j -> bit position in X's / Y's element index
     uint8_t permX[16];                // load order: bit j of the X-tile slot id -> tile coord bit
     uint8_t permY[16];                //   (coord id < TMB: x/y bit, else TMB + k bit)
+    // shared-memory element strides of the two tiles.  The tile dimension that is contiguous in HBM is also made
+    // contiguous in shared memory: the two 16-byte halves of a 32-byte sector then land side by side and one
+    // LDGSTS sector request serves both lanes (otherwise every sector is requested twice).  Both layouts give
+    // conflict-free LDS.128 fragment reads: [k][x] with row stride T+2, or [x][k] with row stride TK+4 (== 4 mod 8).
+    uint16_t xsX, xsK, ysY, ysK;
 };
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, const double a, const double b) {
@@ -79,7 +84,7 @@ __device__ __forceinline__ uint32_t hitab_lookup(const HiTab &tab, uint32_t v, i
     return o;
 }
 
-template <int WX, int WY, int FX, int FY, int TK, int STAGES>
+template <int WX, int WY, int FX, int FY, int TK, int STAGES, int MODE3M = 0>
 struct GettCfg {
     static constexpr int NW = WX * WY;                        // math warps; one more warpgroup (4 warps) produces
     static constexpr int NPT = 128;                           // producer threads
@@ -88,8 +93,10 @@ struct GettCfg {
     // (8 math warps: 3 warps/scheduler x 168 = 504 = 2 x 224 + 56;  16 math warps: 5 x 96 = 480 = 4 x 104 + 64)
     static constexpr int MATH_REGS = NW == 8 ? 224 : 104, PROD_REGS = NW == 8 ? 56 : 64;
     static constexpr int TM = WX * FX * 8, TN = WY * FY * 8;
-    static constexpr int LDX = TM + 2, LDY = TN + 2;          // +2 (x16 B): conflict-free LDS.128 fragments
-    static constexpr int XS = TK * LDX, YS = TK * LDY;        // elements per stage
+    static constexpr int LDX = TM + 2, LDY = TN + 2;          // [k][x] layout: +2 (x16 B) keeps LDS.128 fragments conflict-free
+    static constexpr int LDK = (TK % 8 == 0) ? TK + 4 : TK;   // [x][k] layout: row stride == 4 (mod 8)
+    static constexpr int XS = (TK * LDX > TM * LDK) ? TK * LDX : TM * LDK;        // elements per stage (either layout fits)
+    static constexpr int YS = (TK * LDY > TN * LDK) ? TK * LDY : TN * LDK;
     static constexpr int STAGE_ELEMS = XS + YS;
     static constexpr int XROUNDS = (TM * TK + NPT - 1) / NPT, YROUNDS = (TN * TK + NPT - 1) / NPT;
     static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 2 * XROUNDS + 2 * YROUNDS;   // uint32 tables
@@ -125,10 +132,14 @@ template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile
 // Warp-specialised: warps 0..NW-1 do LDS + DMMA + the C stores, the last warpgroup only gathers tiles (cp.async)
 // and signals "full" mbarriers; math warps hand stages back through "empty" mbarriers.  The math pipe never waits
 // for address arithmetic or load issue, and the gather of the next tiles proceeds under the epilogue stores.
-template <int WX, int WY, int FX, int FY, int TK, int STAGES>
+// MODE3M = 1: the complex product uses three real DMMAs per tile pair instead of four (Karatsuba / "3M":
+//   T1 = Xr*Yr, T2 = Xi*Yi, T3 = (Xr+Xi)*(Yr+Yi);  Re = T1 - T2, Im = T3 - T1 - T2), 25 % less tensor-pipe work for
+// the same algorithmic 8*U flops, at the price of a third accumulator set.
+template <int WX, int WY, int FX, int FY, int TK, int STAGES, int MODE3M = 0>
 __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams p) {
-    using Cfg = GettCfg<WX, WY, FX, FY, TK, STAGES>;
-    constexpr int NW = Cfg::NW, NT = Cfg::NT, TM = Cfg::TM, TN = Cfg::TN, LDX = Cfg::LDX, LDY = Cfg::LDY;
+    using Cfg = GettCfg<WX, WY, FX, FY, TK, STAGES, MODE3M>;
+    constexpr int NW = Cfg::NW, NT = Cfg::NT, TM = Cfg::TM, TN = Cfg::TN;
+    const uint32_t xsX = p.xsX, xsK = p.xsK, ysY = p.ysY, ysK = p.ysK;
     constexpr int TMB = ilog2(TM), TNB = ilog2(TN), TKB = ilog2(TK);
     constexpr int XROUNDS = Cfg::XROUNDS, YROUNDS = Cfg::YROUNDS;
 
@@ -187,14 +198,14 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         const uint32_t w = coordOf((uint32_t)r << 7, p.permX, XEB);
         const uint32_t xl = w & (TM - 1), kl = w >> TMB;
         dXo[r] = tXx[xl] + tXk[kl];
-        dXs[r] = (kl * LDX + xl) * 16;
+        dXs[r] = (kl * xsK + xl * xsX) * 16;
     }
     for (int r = tid; r < YROUNDS; r += NT) {
         const uint32_t e = (uint32_t)r << 7;
         const uint32_t wy = e < nYElems ? coordOf(e, p.permY, yeb) : 0u;
         const uint32_t yl = wy & (TN - 1), kly = wy >> TNB;
         dYo[r] = tYy[yl] + tYk[kly];
-        dYs[r] = (kly * LDY + yl) * 16;
+        dYs[r] = (kly * ysK + yl * ysY) * 16;
     }
     __syncthreads();
 
@@ -212,11 +223,11 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
             const uint32_t w = coordOf(ptid & ((1u << XEB) - 1), p.permX, XEB);
             const uint32_t xl = w & (TM - 1), kl = w >> TMB;
             xOff0 = tXx[xl] + tXk[kl];
-            xSm0 = (kl * LDX + xl) * 16;
+            xSm0 = (kl * xsK + xl * xsX) * 16;
             const uint32_t wy = coordOf(ptid & (nYElems - 1), p.permY, yeb);
             const uint32_t yl = wy & (TN - 1), kly = wy >> TNB;
             yOff0 = tYy[yl] + tYk[kly];
-            ySm0 = (Cfg::XS + kly * LDY + yl) * 16;
+            ySm0 = (Cfg::XS + kly * ysK + yl * ysY) * 16;
         }
         const int yRounds = (int)((nYElems + Cfg::NPT - 1) / Cfg::NPT);
         const bool yLane = ptid < nYElems;
@@ -249,7 +260,9 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
     setmaxnreg_inc<Cfg::MATH_REGS>();
     const int g = lane >> 2, t = lane & 3;
     const int wx0 = (warp % WX) * (FX * 8), wy0 = (warp / WX) * (FY * 8);
-    double accR[FX][FY][2], accI[FX][FY][2];
+    const uint32_t xFrag0 = (wx0 + g) * xsX + t * xsK, yFrag0 = (wy0 + g) * ysY + t * ysK;     // this lane's fragment origin
+    // 4M: accR = Re, accI = Im.   3M: accR = T1, accI = T2, acc3 = T3.
+    double accR[FX][FY][2], accI[FX][FY][2], acc3[MODE3M ? FX : 1][MODE3M ? FY : 1][2];
     uint32_t ti = 0, ch = 0;
 #pragma unroll 1
     for (uint32_t q = 0; q < total; q++) {
@@ -257,40 +270,82 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
 #pragma unroll
             for (int i = 0; i < FX; i++)
 #pragma unroll
-                for (int j = 0; j < FY; j++) { accR[i][j][0] = accR[i][j][1] = accI[i][j][0] = accI[i][j][1] = 0.0; }
+                for (int j = 0; j < FY; j++) {
+                    accR[i][j][0] = accR[i][j][1] = accI[i][j][0] = accI[i][j][1] = 0.0;
+                    if (MODE3M) acc3[i][j][0] = acc3[i][j][1] = 0.0;
+                }
         }
         const uint32_t stage = q % STAGES;
         mbar_wait(barBase + 8 * stage, (q / STAGES) & 1);
-        const double2 *xs = stages + (size_t)stage * Cfg::STAGE_ELEMS;
-        const double2 *ys = xs + Cfg::XS;
+        const double2 *xs_ = stages + (size_t)stage * Cfg::STAGE_ELEMS;
+        const double2 *ys_ = xs_ + Cfg::XS;
+        if (MODE3M) {
+            // software-pipelined: the fragments (and their re+im sums, which need the FP64 pipe the DMMAs saturate)
+            // of k-step kk+1 are fetched while the DMMAs of k-step kk issue, so no DADD sits on the critical path
+            double2 xf[2][FX], yf[2][FY];
+            double xs[2][FX], ys[2][FY];
 #pragma unroll
-        for (int kk = 0; kk < TK / 4; kk++) {
-            double2 xf[FX], yf[FY];
+            for (int i = 0; i < FX; i++) { xf[0][i] = xs_[xFrag0 + i * 8 * xsX]; xs[0][i] = xf[0][i].x + xf[0][i].y; }
 #pragma unroll
-            for (int i = 0; i < FX; i++) xf[i] = xs[(kk * 4 + t) * LDX + wx0 + i * 8 + g];
+            for (int j = 0; j < FY; j++) { yf[0][j] = ys_[yFrag0 + j * 8 * ysY]; ys[0][j] = yf[0][j].x + yf[0][j].y; }
 #pragma unroll
-            for (int j = 0; j < FY; j++) yf[j] = ys[(kk * 4 + t) * LDY + wy0 + j * 8 + g];
-            // four passes over the FX x FY accumulator tiles, one per real product: consecutive DMMAs never
-            // touch the same accumulator (a dependent pair is FX*FY issues apart)
-            double nxi[FX];
+            for (int kk = 0; kk < TK / 4; kk++) {
+                const int cur = kk & 1, nxt = cur ^ 1;
+                if (kk + 1 < TK / 4) {
 #pragma unroll
-            for (int i = 0; i < FX; i++) nxi[i] = dneg(xf[i].y);
+                    for (int i = 0; i < FX; i++) xf[nxt][i] = xs_[xFrag0 + (kk + 1) * 4 * xsK + i * 8 * xsX];
 #pragma unroll
-            for (int i = 0; i < FX; i++)
+                    for (int j = 0; j < FY; j++) yf[nxt][j] = ys_[yFrag0 + (kk + 1) * 4 * ysK + j * 8 * ysY];
+                }
 #pragma unroll
-                for (int j = 0; j < FY; j++) dmma884(accR[i][j][0], accR[i][j][1], xf[i].x, yf[j].x);
+                for (int i = 0; i < FX; i++)
 #pragma unroll
-            for (int i = 0; i < FX; i++)
+                    for (int j = 0; j < FY; j++) dmma884(accR[i][j][0], accR[i][j][1], xf[cur][i].x, yf[cur][j].x);
 #pragma unroll
-                for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].x, yf[j].y);
+                for (int i = 0; i < FX; i++)
 #pragma unroll
-            for (int i = 0; i < FX; i++)
+                    for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[cur][i].y, yf[cur][j].y);
+                if (kk + 1 < TK / 4) {
 #pragma unroll
-                for (int j = 0; j < FY; j++) dmma884(accR[i][j][0], accR[i][j][1], nxi[i], yf[j].y);
+                    for (int i = 0; i < FX; i++) xs[nxt][i] = xf[nxt][i].x + xf[nxt][i].y;
 #pragma unroll
-            for (int i = 0; i < FX; i++)
+                    for (int j = 0; j < FY; j++) ys[nxt][j] = yf[nxt][j].x + yf[nxt][j].y;
+                }
 #pragma unroll
-                for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].y, yf[j].x);
+                for (int i = 0; i < FX; i++)
+#pragma unroll
+                    for (int j = 0; j < FY; j++) dmma884(acc3[i][j][0], acc3[i][j][1], xs[cur][i], ys[cur][j]);
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < TK / 4; kk++) {
+                double2 xf[FX], yf[FY];
+#pragma unroll
+                for (int i = 0; i < FX; i++) xf[i] = xs_[xFrag0 + kk * 4 * xsK + i * 8 * xsX];
+#pragma unroll
+                for (int j = 0; j < FY; j++) yf[j] = ys_[yFrag0 + kk * 4 * ysK + j * 8 * ysY];
+                // four passes over the FX x FY accumulator tiles, one per real product: consecutive DMMAs never
+                // touch the same accumulator (a dependent pair is FX*FY issues apart)
+                double nxi[FX];
+#pragma unroll
+                for (int i = 0; i < FX; i++) nxi[i] = dneg(xf[i].y);
+#pragma unroll
+                for (int i = 0; i < FX; i++)
+#pragma unroll
+                    for (int j = 0; j < FY; j++) dmma884(accR[i][j][0], accR[i][j][1], xf[i].x, yf[j].x);
+#pragma unroll
+                for (int i = 0; i < FX; i++)
+#pragma unroll
+                    for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].x, yf[j].y);
+#pragma unroll
+                for (int i = 0; i < FX; i++)
+#pragma unroll
+                    for (int j = 0; j < FY; j++) dmma884(accR[i][j][0], accR[i][j][1], nxi[i], yf[j].y);
+#pragma unroll
+                for (int i = 0; i < FX; i++)
+#pragma unroll
+                    for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].y, yf[j].x);
+            }
         }
         // stage consumed: hand it back to the producer
         __syncwarp();
@@ -306,8 +361,15 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
 #pragma unroll
                 for (int j = 0; j < FY; j++) {
                     const int y0 = wy0 + j * 8 + 2 * t;
-                    if ((uint32_t)y0 < nyValid) cb[ox + tCy[y0]] = make_double2(accR[i][j][0], accI[i][j][0]);
-                    if ((uint32_t)(y0 + 1) < nyValid) cb[ox + tCy[y0 + 1]] = make_double2(accR[i][j][1], accI[i][j][1]);
+                    double re0, im0, re1, im1;
+                    if (MODE3M) {
+                        re0 = accR[i][j][0] - accI[i][j][0]; im0 = acc3[i][j][0] - accR[i][j][0] - accI[i][j][0];
+                        re1 = accR[i][j][1] - accI[i][j][1]; im1 = acc3[i][j][1] - accR[i][j][1] - accI[i][j][1];
+                    } else {
+                        re0 = accR[i][j][0]; im0 = accI[i][j][0]; re1 = accR[i][j][1]; im1 = accI[i][j][1];
+                    }
+                    if ((uint32_t)y0 < nyValid) cb[ox + tCy[y0]] = make_double2(re0, im0);
+                    if ((uint32_t)(y0 + 1) < nyValid) cb[ox + tCy[y0 + 1]] = make_double2(re1, im1);
                 }
             }
             ch = 0; ++ti;
