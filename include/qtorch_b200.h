@@ -148,6 +148,11 @@ typedef struct qtb_step_trace {
     int32_t rank_a, rank_b, k, kernel;   /* kernel: 0 micro-group, 1 generic, 2 tiled DMMA, 3 streaming */
     float ms;
 } qtb_step_trace;
+/* Largest step (4^n complex multiply-adds, n = 0..8) that may ride in a grouped micro-step launch.  A micro-step runs
+ * on one SM, so the limit trades launch count against single-SM load bandwidth: default 6; callers that evaluate many
+ * independent plans side by side (qtb_plans_run_batched) raise it to 8 before creating their plans.                 */
+int qtb_ctx_set_micro_limit(qtb_ctx *ctx, int log4_units);
+int qtb_ctx_get_micro_limit(qtb_ctx *ctx);
 /* CUDA-event stopwatch on the ctx stream (bench.py times the hot path with it): start flushes deferred work
  * and records an event; stop flushes, records, waits and returns the elapsed milliseconds.             */
 int qtb_ctx_timer_start(qtb_ctx *ctx);

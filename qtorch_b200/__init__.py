@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "qtb_plan_create", "qtb_plan_destroy", "qtb_plan_run_host", "qtb_plan_upload_inputs",
     "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_stage_inputs", "qtb_plan_run_device_slot", "qtb_plans_run_batched", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
     "qtb_comm_unique_id", "qtb_comm_init", "qtb_comm_destroy", "qtb_allreduce_sum",
-    "qtb_ctx_stats", "qtb_ctx_reset_stats", "qtb_ctx_timer_start", "qtb_ctx_timer_stop", "qtb_ctx_trace_enable", "qtb_ctx_trace_read",
+    "qtb_ctx_stats", "qtb_ctx_reset_stats", "qtb_ctx_timer_start", "qtb_ctx_timer_stop", "qtb_ctx_set_micro_limit", "qtb_ctx_get_micro_limit", "qtb_ctx_trace_enable", "qtb_ctx_trace_read",
 ]
 
 
@@ -95,6 +95,8 @@ def load_library():
     L.qtb_plan_read_output.argtypes = [vp, vp, vp]
     L.qtb_plan_stage_inputs.argtypes = [vp, vp, ci, ctypes.POINTER(vp)]
     L.qtb_plan_run_device_slot.argtypes = [vp, vp, ci]
+    L.qtb_ctx_set_micro_limit.argtypes = [vp, ci]
+    L.qtb_ctx_get_micro_limit.argtypes = [vp]
     L.qtb_ctx_timer_start.argtypes = [vp]
     L.qtb_ctx_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.qtb_plan_output_rank.argtypes = [vp]
@@ -268,6 +270,9 @@ class Engine:
 
     def reset_stats(self):
         _check(self.lib.qtb_ctx_reset_stats(self.ctx))
+
+    def set_micro_limit(self, log4_units):
+        _check(self.lib.qtb_ctx_set_micro_limit(self.ctx, log4_units))
 
     def timer_start(self):
         _check(self.lib.qtb_ctx_timer_start(self.ctx))

@@ -40,7 +40,10 @@ static int fail(int status, const std::string &msg) { g_lastError = msg; return 
 
 // ------------------------------------------------------------------------------------------------
 // kernel families
-static const unsigned long long MICRO_MAX_UNITS = 1ull << 16;   // 4^8 complex MACs: ~1 us on one SM
+// A micro-step runs on ONE SM inside the grouped launch, so its size limit trades launch count against the
+// load bandwidth of a single SM (2 x 16 B per complex MAC): 4^6 MACs by default for latency-bound single plans,
+// raised to 4^8 by callers that run many plans side by side (qtb_ctx_set_micro_limit; the QAOA term dispatcher).
+static const int MICRO_DEFAULT_LOG4 = 6;
 static const int MICRO_MAX_RANK = 7;
 
 struct GettChoice { int cfg; bool swap; };      // cfg: 0 C1/TK16 1 C1/TK4 2 C2/TK16 3 C2/TK4 4 C3/TK16 5 C3/TK4
@@ -115,9 +118,9 @@ static bool disable_micro() {
     return v == 1;
 }
 
-static int choose_kind(const StepGeom &g, GettChoice &gc) {
+static int choose_kind(const StepGeom &g, GettChoice &gc, int microLog4) {
     const unsigned long long U = g.units();
-    if (!disable_micro() && U <= MICRO_MAX_UNITS && g.rA <= MICRO_MAX_RANK && g.rB <= MICRO_MAX_RANK && g.rC <= MICRO_MAX_RANK)
+    if (!disable_micro() && U <= (1ull << (2 * microLog4)) && g.rA <= MICRO_MAX_RANK && g.rB <= MICRO_MAX_RANK && g.rC <= MICRO_MAX_RANK)
         return KIND_MICRO;
     const int bigFree = std::max(g.nfa, g.nfb), smallFree = std::min(g.nfa, g.nfb);
     if (!force_generic() && g.rC <= 2 && g.k >= 6) return KIND_REDUCE;       // long sums, <= 16 outputs: split-K
@@ -326,6 +329,7 @@ struct qtb_ctx_s {
     bool trace = false;
     std::vector<TraceRec> traceRecs;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    int microLog4 = MICRO_DEFAULT_LOG4;
     double *batchOut = nullptr; size_t batchOutCap = 0;      // pinned gather buffer of qtb_plans_run_batched
     // NCCL
     void *comm = nullptr; int nRanks = 1, rank = 0;
@@ -398,7 +402,8 @@ static int launch_generic(qtb_ctx *ctx, const DevStep &st, cudaStream_t s) {
 // ---- micro-batch blob assembly -----------------------------------------------------------------
 // Builds: MicroHeader | levelItemStart | items | steps (copy steps first at level 0) | payload
 static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std::vector<PendingUpload> &ups,
-                               const std::vector<uint8_t> &payload, std::vector<uint8_t> &blob, const uint8_t *devBase) {
+                               const std::vector<uint8_t> &payload, std::vector<uint8_t> &blob, const uint8_t *devBase,
+                               const void *prefetchPtr = nullptr, size_t prefetchBytes = 0) {
     // level 0 = upload copies and steps with no pending producer; a step's level is
     // 1 + max(level of the pending op producing each operand)
     uint32_t nLevels = ups.empty() ? 0 : 1;
@@ -420,7 +425,8 @@ static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std:
     for (const auto &s : steps) {
         all[idx] = s.st;
         const uint32_t NC = 1u << (2 * s.st.rC), K = 1u << (2 * s.st.k);
-        const uint32_t nChunks = (NC >= 32 || K < 16) ? (NC + QTB_MICRO_CHUNK - 1) / QTB_MICRO_CHUNK : 1;
+        const uint32_t nChunks = (NC + QTB_MICRO_CHUNK - 1) / QTB_MICRO_CHUNK;
+        (void)K;
         for (uint32_t c = 0; c < nChunks; c++) perLevel[s.level].push_back({idx, c});
         idx++;
     }
@@ -434,7 +440,9 @@ static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std:
     const size_t payloadOff = off;
     off += payload.size();
     blob.assign(off, 0);
-    MicroHeader hdr{nLevels, nItems, nSteps, (uint32_t)stepsOff};
+    MicroHeader hdr{nLevels, nItems, nSteps, (uint32_t)stepsOff, (uint32_t)payloadOff, 0u, 0ull};
+    if (prefetchPtr && prefetchBytes) { hdr.prefetchPtr = (uint64_t)prefetchPtr; hdr.prefetchBytes = (uint32_t)std::min<size_t>(prefetchBytes, 8u << 20); }
+    else if (!payload.empty() && devBase) { hdr.prefetchPtr = (uint64_t)(devBase + payloadOff); hdr.prefetchBytes = (uint32_t)payload.size(); }
     memcpy(blob.data(), &hdr, sizeof(hdr));
     uint32_t *lis = reinterpret_cast<uint32_t *>(blob.data() + sizeof(MicroHeader));
     MicroItem *items = reinterpret_cast<MicroItem *>(lis + nLevels + 1);
@@ -488,7 +496,7 @@ static int flush_locked(qtb_ctx *ctx) {
     if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
     CU(cudaMemcpyAsync(ctx->ringDev + off, ctx->ringHost + off, blob.size(), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.bytes_h2d += (long long)blob.size();
-    k_micro<<<1, QTB_MICRO_THREADS, 0, ctx->stream>>>(ctx->ringDev + off, ctx->zeroOffsetDev);
+    k_micro<<<1, QTB_MICRO_THREADS, QTB_MICRO_SMEM, ctx->stream>>>(ctx->ringDev + off, ctx->zeroOffsetDev);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ringEvent, ctx->stream));
     ctx->ringEventValid = true;
@@ -565,6 +573,7 @@ int qtb_ctx_create(int device, qtb_ctx **out) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { delete ctx; return fail(QTB_ERR_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only"); }
     ctx->numSMs = prop.multiProcessorCount;
+    if (const char *e = getenv("QTB_MICRO_LOG4")) ctx->microLog4 = std::max(0, std::min(8, atoi(e)));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaMallocHost((void **)&ctx->ringHost, ctx->ringSize));
     CU(cudaMalloc((void **)&ctx->ringDev, ctx->ringSize));
@@ -573,6 +582,7 @@ int qtb_ctx_create(int device, qtb_ctx **out) {
     CU(cudaMalloc((void **)&ctx->reduceScratch, (size_t)REDUCE_MAX_BLOCKS * 16 * sizeof(double2)));
     CU(cudaMemset(ctx->zeroOffsetDev, 0, 8));
     CU(cudaEventCreateWithFlags(&ctx->ringEvent, cudaEventDisableTiming));
+    CU(cudaFuncSetAttribute(k_micro, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QTB_MICRO_SMEM));
     for (auto &inst : g_gett) {
         CU(cudaFuncSetAttribute(inst.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inst.smem));
         int occ = 1;
@@ -699,7 +709,7 @@ int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos
     ST(ensure_device(ctx));
     ST(ensure_buffer(ctx, c));
     GettChoice gc{0, false};
-    const int kind = choose_kind(g, gc);
+    const int kind = choose_kind(g, gc, ctx->microLog4);
     ctx->stats.steps++;
     ctx->stats.units += (long long)g.units();
     if (kind == KIND_MICRO) {
@@ -760,6 +770,14 @@ int qtb_ctx_timer_stop(qtb_ctx *ctx, float *ms) {
     CU(cudaEventElapsedTime(ms, ctx->timer0, ctx->timer1));
     return QTB_OK;
 }
+int qtb_ctx_set_micro_limit(qtb_ctx *ctx, int log4Units) {
+    if (!ctx || log4Units < 0 || log4Units > 8) return fail(QTB_ERR_INVALID, "micro limit must be 0..8 (4^n complex MACs)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(flush_locked(ctx));
+    ctx->microLog4 = log4Units;
+    return QTB_OK;
+}
+int qtb_ctx_get_micro_limit(qtb_ctx *ctx) { return ctx ? ctx->microLog4 : -1; }
 int qtb_ctx_trace_enable(qtb_ctx *ctx, int on) {
     if (!ctx) return fail(QTB_ERR_INVALID, "null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);

@@ -114,23 +114,66 @@ __global__ void __launch_bounds__(256) k_step_warp(const DevStep st) {
 #define QTB_MICRO_CHUNK 128
 #define QTB_MICRO_THREADS 1024
 
-struct MicroHeader { uint32_t nLevels, nItems, nSteps, stepsOffset; };
+struct MicroHeader {
+    uint32_t nLevels, nItems, nSteps, stepsOffset;
+    uint32_t controlBytes;        // header + level table + items + steps (what the kernel stages in shared memory)
+    uint32_t prefetchBytes;       // size of the operand region to pull into L2 up front (0 = none)
+    uint64_t prefetchPtr;         // device address of that region (plan input blob / upload payload)
+};
 struct MicroItem { uint32_t step; uint32_t chunk; };
+
+// per-warp scratch in dynamic shared memory: the step descriptor (so leg tables are not re-read from global memory
+// for every index) and the offsets of all summed terms when K <= QTB_MICRO_TAB
+#define QTB_MICRO_TAB 256
+struct MicroWarpScratch {
+    DevStep st;
+    uint32_t sumA[QTB_MICRO_TAB], sumB[QTB_MICRO_TAB];
+};
+static_assert(sizeof(DevStep) % 4 == 0, "DevStep is copied word-wise");
+#define QTB_MICRO_CTRL_BYTES (96 * 1024)       // control structures up to this size are staged in shared memory
+#define QTB_MICRO_SMEM ((QTB_MICRO_THREADS / 32) * sizeof(MicroWarpScratch) + QTB_MICRO_CTRL_BYTES)
 
 __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *__restrict__ blobBase,
                                                                   const uint64_t *__restrict__ blobOffsets) {
+    extern __shared__ __align__(16) uint8_t microSmem[];
     const uint8_t *blob = blobBase + blobOffsets[blockIdx.x];
     const MicroHeader hdr = *reinterpret_cast<const MicroHeader *>(blob);
-    const uint32_t *lis = reinterpret_cast<const uint32_t *>(blob + sizeof(MicroHeader));
-    const MicroItem *items = reinterpret_cast<const MicroItem *>(lis + hdr.nLevels + 1);
-    const DevStep *steps = reinterpret_cast<const DevStep *>(blob + hdr.stepsOffset);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    MicroWarpScratch &ws = reinterpret_cast<MicroWarpScratch *>(microSmem)[warp];
+    // A launch usually starts cold (the big steps in between stream gigabytes through L2), and every item would
+    // otherwise chase item -> descriptor -> operand through DRAM one round trip at a time: stage the control
+    // structures in shared memory with one cooperative read and pull the operand region into L2 meanwhile.
+    uint8_t *ctrl = microSmem + (QTB_MICRO_THREADS / 32) * sizeof(MicroWarpScratch);
+    const bool staged = hdr.controlBytes <= QTB_MICRO_CTRL_BYTES;
+    if (staged) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+        uint4 *dst = reinterpret_cast<uint4 *>(ctrl);
+        for (uint32_t i = threadIdx.x; i < (hdr.controlBytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    if (hdr.prefetchBytes) {
+        const uint8_t *pf = reinterpret_cast<const uint8_t *>(hdr.prefetchPtr);
+        for (uint32_t off = threadIdx.x * 128u; off < hdr.prefetchBytes; off += blockDim.x * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + off));
+    }
+    __syncthreads();
+    const uint8_t *cb = staged ? ctrl : blob;
+    const uint32_t *lis = reinterpret_cast<const uint32_t *>(cb + sizeof(MicroHeader));
+    const MicroItem *items = reinterpret_cast<const MicroItem *>(lis + hdr.nLevels + 1);
+    const DevStep *steps = reinterpret_cast<const DevStep *>(cb + hdr.stepsOffset);
 
     for (uint32_t lvl = 0; lvl < hdr.nLevels; lvl++) {
         const uint32_t i0 = lis[lvl], i1 = lis[lvl + 1];
         for (uint32_t it = i0 + warp; it < i1; it += nw) {
             const MicroItem item = items[it];
-            const DevStep &st = steps[item.step];
+            // descriptor -> this warp's shared-memory slot (one coalesced read)
+            __syncwarp();
+            {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(&steps[item.step]);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(&ws.st);
+                for (int w = lane; w < (int)(sizeof(DevStep) / 4); w += 32) dst[w] = src[w];
+            }
+            __syncwarp();
+            const DevStep &st = ws.st;
             const uint32_t NC = 1u << (2 * st.rC), K = 1u << (2 * st.k);
             // plain (coherent) loads: operands may have been written earlier in this launch
             const double2 *A = st.A;
@@ -144,37 +187,47 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
                     const uint32_t e = item.chunk * QTB_MICRO_CHUNK + j * 32 + lane;
                     if (e < elems) st.C[e] = A[e];
                 }
-            } else if (NC >= 32 || K < 16) {
-                // lanes over outputs
-#pragma unroll 1
-                for (int j = 0; j < QTB_MICRO_CHUNK / 32; j++) {
-                    const uint32_t c = item.chunk * QTB_MICRO_CHUNK + j * 32 + lane;
-                    if (c < NC) {
-                        uint64_t ba, bb;
-                        free_offsets(st, c, ba, bb);
-                        double cr = 0.0, ci = 0.0;
-                        for (uint32_t s = 0; s < K; s++) {
-                            uint64_t oa, ob;
-                            sum_offsets(st, s, oa, ob);
-                            cmac(cr, ci, A[ba + oa], B[bb + ob]);
-                        }
-                        st.C[c] = make_double2(cr, ci);
-                    }
+                continue;
+            }
+            const bool tabled = K <= QTB_MICRO_TAB;
+            if (tabled) {
+                for (uint32_t s = lane; s < K; s += 32) {
+                    uint64_t oa, ob;
+                    sum_offsets(st, s, oa, ob);
+                    ws.sumA[s] = (uint32_t)oa; ws.sumB[s] = (uint32_t)ob;
                 }
-            } else {
-                // few outputs, longer sums: lanes over the summed index
-                for (uint32_t c = 0; c < NC; c++) {
+                __syncwarp();
+            }
+            // lane layout: NC >= 32 -> one output per lane (4 passes per 128-output chunk); NC < 32 -> the 32 lanes
+            // cover (output, slice of the summed index) and a shuffle tree adds the slices, so tiny results still
+            // use the whole warp.  The summed loop is unrolled so several independent loads are in flight.
+            const uint32_t G = NC >= 32 ? 1u : 32u / NC;                 // lanes per output along s
+            const uint32_t sg = NC >= 32 ? 0u : (uint32_t)lane / NC;
+            const int passes = NC >= 32 ? QTB_MICRO_CHUNK / 32 : 1;
+#pragma unroll 1
+            for (int j = 0; j < passes; j++) {
+                const uint32_t c = NC >= 32 ? item.chunk * QTB_MICRO_CHUNK + j * 32 + lane : ((uint32_t)lane & (NC - 1));
+                double cr = 0.0, ci = 0.0;
+                if (c < NC) {
                     uint64_t ba, bb;
                     free_offsets(st, c, ba, bb);
-                    double cr = 0.0, ci = 0.0;
-                    for (uint32_t s = lane; s < K; s += 32) {
-                        uint64_t oa, ob;
-                        sum_offsets(st, s, oa, ob);
-                        cmac(cr, ci, A[ba + oa], B[bb + ob]);
+                    const double2 *pa = A + ba, *pb = B + bb;
+                    if (tabled) {
+#pragma unroll 4
+                        for (uint32_t s = sg; s < K; s += G) cmac(cr, ci, pa[ws.sumA[s]], pb[ws.sumB[s]]);
+                    } else {
+                        for (uint32_t s = sg; s < K; s += G) {
+                            uint64_t oa, ob;
+                            sum_offsets(st, s, oa, ob);
+                            cmac(cr, ci, pa[oa], pb[ob]);
+                        }
                     }
-                    cr = warp_sum(cr); ci = warp_sum(ci);
-                    if (lane == 0) st.C[c] = make_double2(cr, ci);
                 }
+                for (uint32_t off = NC; off < 32; off <<= 1) {           // no-op when NC >= 32
+                    cr += __shfl_xor_sync(0xffffffffu, cr, off);
+                    ci += __shfl_xor_sync(0xffffffffu, ci, off);
+                }
+                if (c < NC && sg == 0) st.C[c] = make_double2(cr, ci);
             }
         }
         __syncthreads();

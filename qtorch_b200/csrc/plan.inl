@@ -42,7 +42,7 @@ static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, s)); }
         if (sg.micro) {
-            k_micro<<<1, QTB_MICRO_THREADS, 0, s>>>(pl->microBlobDev, pl->segOffsetsDev + sg.microIndex);
+            k_micro<<<1, QTB_MICRO_THREADS, QTB_MICRO_SMEM, s>>>(pl->microBlobDev, pl->segOffsetsDev + sg.microIndex);
             CU(cudaGetLastError());
             ctx->stats.launches++;
         } else {
@@ -126,7 +126,7 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
         const qtb_plan_step &s = steps[i];
         const StepGeom &g = geoms[i];
         GettChoice gc{0, false};
-        const int kind = choose_kind(g, gc);
+        const int kind = choose_kind(g, gc, ctx->microLog4);
         void *cp = nullptr;
         { int st = pl->pool.alloc(g.rC, &cp); if (st != QTB_OK) return bail(st); }
         dev[nInputs + i] = (double2 *)cp;
@@ -162,7 +162,7 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
         for (size_t m = 0; m < microBlobs.size(); m++) {
             std::vector<PendingStep> st(microBlobs[m].size() / sizeof(PendingStep));
             memcpy(st.data(), microBlobs[m].data(), microBlobs[m].size());
-            build_micro_blob(st, {}, {}, built[m], nullptr);
+            build_micro_blob(st, {}, {}, built[m], nullptr, m == 0 ? pl->inBlobDev : nullptr, m == 0 ? pl->inBlobBytes : 0);
             offs[m] = total;
             total += (built[m].size() + 255) & ~(size_t)255;
         }
@@ -327,7 +327,7 @@ int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const dou
         uint64_t *addr = reinterpret_cast<uint64_t *>(ctx->ringHost + off);
         for (int i = 0; i < n; i++) addr[i] = reinterpret_cast<uint64_t>(plans[i]->microBlobDev);
         CU(cudaMemcpyAsync(ctx->ringDev + off, ctx->ringHost + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        k_micro<<<n, QTB_MICRO_THREADS, 0, ctx->stream>>>(nullptr, reinterpret_cast<const uint64_t *>(ctx->ringDev + off));
+        k_micro<<<n, QTB_MICRO_THREADS, QTB_MICRO_SMEM, ctx->stream>>>(nullptr, reinterpret_cast<const uint64_t *>(ctx->ringDev + off));
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ringEvent, ctx->stream));
         ctx->ringEventValid = true;

@@ -133,7 +133,11 @@ inline bool LineGraph::LGContract() {
     }
     // contract wire by wire; a wire already summed by an earlier step (parallel wires) is skipped
     for (int w1 : order) {
-        if (w1 < 1 || w1 > static_cast<int>(GraphWires.size())) throw QbbFailure();
+        // QuickBB leaves isolated line-graph vertices out of its ordering, so the line can hold fewer numbers than
+        // there are wires; the reference then indexes GraphWires[-1] (LineGraph.h:328-360, undefined behaviour that
+        // happens to be harmless).  Skip such entries: the untouched components surface below as ContractionFailure,
+        // exactly the reference's outcome for disconnected networks.
+        if (w1 < 1 || w1 > static_cast<int>(GraphWires.size())) continue;
         std::shared_ptr<Wire> w = GraphWires[w1 - 1];
         if (!w->IsContracted()) origNetwork->ContractNodes(w->GetNodeA().lock(), w->GetNodeB().lock(), 100);
     }

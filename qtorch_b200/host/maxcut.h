@@ -144,7 +144,17 @@ public:
         for (size_t e = static_cast<size_t>(rank); e < mData.pairs.size(); e += static_cast<size_t>(world)) mOwned.push_back(static_cast<int>(e));
         std::vector<double> bg(2 * mData.p);
         for (int i = 0; i < mData.p; ++i) { bg[i] = 0.392699; bg[i + mData.p] = 0.785399; }      // maxcut.cpp:155-157
-        for (int e : mOwned) mTerms.push_back(BuildTerm(e, bg, planTries));
+        // many small plans evaluated side by side (one CTA each): let larger steps ride in the grouped launch
+        qtb_ctx *ctx = device::Engine::Get().ctx();
+        const int before = qtb_ctx_get_micro_limit(ctx);
+        device::check(qtb_ctx_set_micro_limit(ctx, 8));
+        try {
+            for (int e : mOwned) mTerms.push_back(BuildTerm(e, bg, planTries));
+        } catch (...) {
+            qtb_ctx_set_micro_limit(ctx, before);
+            throw;
+        }
+        device::check(qtb_ctx_set_micro_limit(ctx, before));
     }
     ~QaoaObjective() {
         if (device::Engine::Get().alive())

@@ -35,7 +35,8 @@ def _run(name, tmp_path, extra_env=None, steps=False):
 @pytest.mark.parametrize("name", SMALL)
 def test_network_value_matches_reference(built, name, tmp_path):
     rec, out = _run(name, tmp_path)
-    assert "exception" not in out, out.get("exception")
+    # disconnected networks make the line-graph path fail in the reference too (ContractionFailure, partial value kept)
+    assert out.get("exception") == rec.get("exception"), out.get("exception")
     val = complex(float(out["value"][0]), float(out["value"][1]))
     assert _close(val, rec["value"]), (val, rec["value"])
     assert out["plan"] == rec["plan"] and int(out["flops"][0]) == rec["flops"]

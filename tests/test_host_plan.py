@@ -22,6 +22,7 @@ def test_linegraph_plan_identical_to_reference(built, name):
     cwd, qasm, meas, ordering = golden_paths(rec)
     out = qt.run_harness(["lg", qasm, meas, ordering, rec["reduce"]], plan_only=True, cwd=cwd)
     assert int(out["ok"][0]) == rec["ok"]
+    assert out.get("exception") == rec.get("exception")
     assert out["plan"] == rec["plan"]
     assert int(out["flops"][0]) == rec["flops"]
     assert int(out["nodes"][0]) == rec["nodes"]

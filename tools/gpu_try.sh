@@ -1,14 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-P="timeout 90 python tools/prof_step.py"
-echo "== 3M 16 warps pipelined" | tee gpurun_out/try.log
-QTB_GETT_C1=2 $P 10 10 3 0 2 5 1 7 6 3 | tail -1 | tee -a gpurun_out/try.log
-QTB_GETT_C1=2 $P 6 14 3 0 2 3 2 7 9 3 | tail -1 | tee -a gpurun_out/try.log
-echo "== 3M 8 fat warps pipelined" | tee -a gpurun_out/try.log
-QTB_GETT_C1=3 $P 10 10 3 0 2 5 1 7 6 3 | tail -1 | tee -a gpurun_out/try.log
-QTB_GETT_C1=3 $P 6 14 3 0 2 3 2 7 9 3 | tail -1 | tee -a gpurun_out/try.log
-QTB_GETT_C1=3 $P 9 11 3 0 4 6 6 8 5 3 | tail -1 | tee -a gpurun_out/try.log
-QTB_GETT_C1=3 $P 9 9 2 0 4 6 8 3 | tail -1 | tee -a gpurun_out/try.log
-QTB_GETT_C1=2 timeout 600 python -m pytest tests -x -q -m gpu --timeout 300 -k "gett or config2 or plan_api or linearity" 2>&1 | tail -2 | tee -a gpurun_out/try.log
-QTB_GETT_C1=3 timeout 600 python -m pytest tests -x -q -m gpu --timeout 300 -k "gett or config2 or plan_api or linearity" 2>&1 | tail -2 | tee -a gpurun_out/try.log
+for L in 5 6 7; do
+echo "== QTB_MICRO_LOG4=$L" | tee -a gpurun_out/try.log
+QTB_MICRO_LOG4=$L timeout 600 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_m$L.log
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_m$L.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['plan_launches_per_term'], d['kernel_time_ms_by_kind'], 'sliced ms', d['sliced']['ms_per_amplitude'], d['sliced']['matches_reference_1e-10'])
+PY
+done
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "not drop_in" 2>&1 | tail -3 | tee -a gpurun_out/try.log
+timeout 500 python tools/bench_configs.py 2>&1 | grep "^{" | tee gpurun_out/configs.jsonl | cut -c1-250
