@@ -1,0 +1,73 @@
+"""The drop-in front-ends on the GPU: `qtorch <script.inp>` must write the same result file as the reference binary
+(oracle/_ref/qtorch_ref, the unmodified src/main.cpp) for the same script and frozen ordering; `maxcutQAOA` mode 0 must
+improve the objective from the reference's start angles and leave the angle file behind."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+import qtorch_b200 as qt
+
+pytestmark = pytest.mark.gpu
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "qtorch_ref")
+
+
+def _workdir(tmp_path, ordering):
+    work = os.path.join(str(tmp_path), "w")
+    os.makedirs(os.path.join(work, "output"))
+    shutil.copytree(os.path.join(GOLDEN, "Samples"), os.path.join(work, "Samples"))
+    shutil.copy(os.path.join(GOLDEN, "orderings", ordering), os.path.join(work, "output", "qbb.out"))
+    return work
+
+
+def _script(work, name, qasm, measure, method="linegraph-qbb", extra=""):
+    path = os.path.join(work, name + ".inp")
+    open(path, "w").write("# test script\n>int threads 8\n>string qasm %s\n>string measurement %s\n>string contractmethod %s\n"
+                          ">bool readqbbresonly true\n>string outputpath %s.out\n%s" % (qasm, measure, method, name, extra))
+    return path
+
+
+def _result_lines(path):
+    lines = open(path).read().splitlines()
+    return [l for l in lines if not l.startswith("Contraction complete")]        # that line carries the wall time
+
+
+@pytest.mark.parametrize("qasm,measure,ordering", [("Samples/qft8.qasm", "Samples/measureSampleOne.txt", "qft8_X8.qbb.out"),
+                                                  ("Samples/test_JW.qasm", "Samples/measureSampleOne.txt", "testJW_XXXX.qbb.out")])
+def test_qtorch_cli_matches_reference_binary(built, tmp_path, qasm, measure, ordering):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/qtorch_ref not built")
+    work = _workdir(tmp_path, ordering)
+    env = dict(os.environ)
+    mine = subprocess.run([qt.CLI_PATH, _script(work, "mine", qasm, measure)], cwd=work, capture_output=True, text=True, timeout=300, env=env)
+    # the reference binary re-reads output/qbb.out as well (readqbbresonly), no QuickBB needed
+    ref = subprocess.run([REF_CLI, _script(work, "ref", qasm, measure)], cwd=work, capture_output=True, text=True, timeout=300, env=env)
+    assert mine.returncode == 0 and ref.returncode == 0, (mine.stdout[-500:], ref.stdout[-500:])
+    a, b = _result_lines(os.path.join(work, "mine.out")), _result_lines(os.path.join(work, "ref.out"))
+    assert a == b and len(a) == 2, (a, b)           # "Result of Contraction: (..)" and "Number of floating point ops ..."
+    assert "Result of Contraction (also printed to file):" in mine.stdout
+
+
+def test_qtorch_cli_stochastic_and_bad_method(built, tmp_path):
+    work = _workdir(tmp_path, "qft8_X8.qbb.out")
+    r = subprocess.run([qt.CLI_PATH, _script(work, "st", "Samples/bell_pair.qasm", "Samples/measureSampleTwo.txt", "simple-stoch")], cwd=work,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and open(os.path.join(work, "st.out")).read().startswith("Result of Contraction: (")
+    r = subprocess.run([qt.CLI_PATH, _script(work, "bad", "Samples/bell_pair.qasm", "Samples/measureSampleTwo.txt", "no-such-method")], cwd=work,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "bad option" in r.stdout
+
+
+def test_maxcut_cli_improves_objective(built, tmp_path):
+    work = os.path.join(str(tmp_path), "m")
+    os.makedirs(work)
+    exe = os.path.join(ROOT, "qtorch_b200", "bin", "maxcutQAOA")
+    r = subprocess.run([exe, os.path.join(GOLDEN, "Samples", "3regRand30Node50.dgf"), "1", "0", "angles.txt", "60"], cwd=work,
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, QTORCH_QUIET="1"))
+    assert r.returncode == 0, r.stdout[-1000:]
+    best = float([l for l in r.stdout.splitlines() if "best F_p" in l][0].split("=")[-1])
+    assert best >= 32.259328920042 - 1e-9            # never worse than the reference's start point (golden F_p)
+    angles = [float(x) for x in open(os.path.join(work, "angles.txt")).read().split()]
+    assert len(angles) == 2

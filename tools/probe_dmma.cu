@@ -85,6 +85,46 @@ __global__ void __launch_bounds__(512) v3(const double2 *in, double *out, int it
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// v5: the 3M loop of k_gett (T1 = Xr*Yr, T2 = Xi*Yi, T3 = (Xr+Xi)*(Yr+Yi)): LDS fragments + DADD sums + 3 DMMA passes.
+// SUMS = 0 drops the DADDs (wrong maths, same DMMA count) to isolate what the FP64 adds cost next to the DMMAs.
+template <int FX, int FY, int SUMS>
+__global__ void __launch_bounds__(512) v5(const double2 *in, double *out, int iters) {
+    extern __shared__ double2 sm[];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = in[i];
+    __syncthreads();
+    double c1[FX][FY][2], c2[FX][FY][2], c3[FX][FY][2];
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = c3[i][j][0] = c3[i][j][1] = 0;
+    for (int it = 0; it < iters; it++) {
+        const int kk = it & 3;
+        double2 xf[FX], yf[FY];
+        double xs[FX], ys[FY];
+#pragma unroll
+        for (int i = 0; i < FX; i++) xf[i] = sm[(kk * 4 + t) * 66 + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < FY; j++) yf[j] = sm[2100 + (kk * 4 + t) * 66 + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < FX; i++) xs[i] = SUMS ? xf[i].x + xf[i].y : xf[i].x;
+#pragma unroll
+        for (int j = 0; j < FY; j++) ys[j] = SUMS ? yf[j].x + yf[j].y : yf[j].y;
+#pragma unroll
+        for (int i = 0; i < FX; i++)
+#pragma unroll
+            for (int j = 0; j < FY; j++) dmma(c1[i][j][0], c1[i][j][1], xf[i].x, yf[j].x);
+#pragma unroll
+        for (int i = 0; i < FX; i++)
+#pragma unroll
+            for (int j = 0; j < FY; j++) dmma(c2[i][j][0], c2[i][j][1], xf[i].y, yf[j].y);
+#pragma unroll
+        for (int i = 0; i < FX; i++)
+#pragma unroll
+            for (int j = 0; j < FY; j++) dmma(c3[i][j][0], c3[i][j][1], xs[i], ys[j]);
+    }
+    double s = 0;
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) s += c1[i][j][0] + c1[i][j][1] + c2[i][j][0] + c2[i][j][1] + c3[i][j][0] + c3[i][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static float time_ms(F f) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -113,5 +153,12 @@ int main() {
     RUN3(4, 2, false, 1, "v3_complex_4x2_4pass_noLDS");
     RUN3(4, 2, true, 1, "v4_complex_4x2_4pass_LDS");
     RUN3(2, 2, true, 1, "v4_complex_2x2_4pass_LDS");
+#define RUN5(FX, FY, S, NAME) \
+    CK(cudaFuncSetAttribute(v5<FX, FY, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    for (int w : {8, 16}) { float ms = time_ms([&] { v5<FX, FY, S><<<nsm, w * 32, smem>>>((const double2 *)in, out, iters); }); rep(NAME, w, 3 * FX * FY, ms); }
+    RUN5(2, 2, 1, "v5_3M_2x2_LDS_DADD");
+    RUN5(2, 2, 0, "v5_3M_2x2_LDS_noDADD");
+    RUN5(4, 2, 1, "v5_3M_4x2_LDS_DADD");
+    RUN5(4, 2, 0, "v5_3M_4x2_LDS_noDADD");
     return 0;
 }
