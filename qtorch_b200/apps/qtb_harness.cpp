@@ -90,6 +90,25 @@ static int mode_lg(int argc, char **argv, bool steps) {
     return 0;
 }
 
+// minfill qasm measure out.qbb reduce : in-process ordering, then contraction along it
+static int mode_minfill(int argc, char **argv, bool steps) {
+    auto net = std::make_shared<Network>(argv[2], argv[3]);
+    if (atoi(argv[5])) net->ReduceCircuit();
+    LineGraph lg(net);
+    lg.SetQBBOutFiles("/dev/null", argv[4], "/dev/null");
+    double t0 = now_s();
+    const int width = lg.runMinFill();
+    double t1 = now_s();
+    bool ok = false;
+    try { ok = lg.LGContract(); } catch (std::exception &e) { printf("@@exception %s\n", e.what()); }
+    cplx v = net->GetFinalValue();
+    printf("@@ok %d\n@@width %d\n@@ordering_seconds %.6f\n", (int)ok, width, t1 - t0);
+    print_value("value", v);
+    printf("@@flops %lld\n", net->getNumFloatOps());
+    if (steps) print_steps(net);
+    return 0;
+}
+
 static int mode_cnf(int argc, char **argv) {
     auto net = std::make_shared<Network>(argv[2], argv[3]);
     if (atoi(argv[5])) net->ReduceCircuit();
@@ -150,6 +169,7 @@ int main(int argc, char **argv) {
         if (m == "gate") return mode_gate(argc, argv);
         if (m == "lg") return mode_lg(argc, argv, steps);
         if (m == "cnf") return mode_cnf(argc, argv);
+        if (m == "minfill") return mode_minfill(argc, argv, steps);
         if (m == "seq") return mode_seq(argc, argv, steps);
         if (m == "stoch") return mode_stoch(argc, argv, steps);
         if (m == "user") return mode_user(argc, argv);

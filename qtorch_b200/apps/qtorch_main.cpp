@@ -77,9 +77,10 @@ int main(int argc, char *argv[]) {
 
     const std::string method = in.mapString["contractmethod"];
     std::cout << "Contraction method: " << method << "\n";
-    if (method == "linegraph-qbb") {
+    if (method == "linegraph-qbb" || method == "linegraph-minfill") {
         std::cout << "Contraction method: Linegraph / tree decomposition\n";
         LineGraph lg(net);
+        const bool inProcessOrdering = method == "linegraph-minfill";      // addition: no external quickbb binary
         if (in.mapString.count("qbbdir")) lg.SetQBBOutDirectory(in.mapString["qbbdir"]);
         const bool sixtyFour = !(in.mapBool.count("64bit") && !in.mapBool["64bit"]);
         const bool onlyOrder = in.mapBool["qbbonly"], onlyContract = !onlyOrder && in.mapBool["readqbbresonly"];
@@ -87,12 +88,15 @@ int main(int argc, char *argv[]) {
             if (onlyOrder) {
                 std::cout << "qbbonly=true. Only running qbb on linegraph, not doing contraction.\n";
                 std::cout << "quickbbseconds set to: " << in.mapInt["quickbbseconds"] << std::endl;
-                lg.runQuickBB(in.mapInt["quickbbseconds"], &clock, sixtyFour);
+                if (inProcessOrdering) std::cout << "In-process min-fill ordering, width " << lg.runMinFill() << std::endl;
+                else lg.runQuickBB(in.mapInt["quickbbseconds"], &clock, sixtyFour);
                 std::cout << "QuickBB has been run. Set qbbonly=false and readqbbresonly=true to contract network. Exiting.\n";
                 return 0;
             }
             if (onlyContract) {
                 std::cout << "readqbbresonly=true. Attempting to read previous qbb result, and contracting network.\n";
+            } else if (inProcessOrdering) {
+                std::cout << "In-process min-fill ordering, width " << lg.runMinFill() << std::endl;
             } else {
                 std::cout << "quickbbseconds set to: " << in.mapInt["quickbbseconds"] << std::endl;
                 lg.runQuickBB(in.mapInt["quickbbseconds"], &clock, sixtyFour);

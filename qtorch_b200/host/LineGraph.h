@@ -11,8 +11,10 @@
 #include <sys/stat.h>
 #include <array>
 #include <cstdio>
+#include <cmath>
 #include <fstream>
 #include <iostream>
+#include <random>
 #include <sstream>
 #include <unordered_map>
 #include <vector>
@@ -28,6 +30,13 @@ public:
     LineGraph(std::shared_ptr<Network> origGraph) { Build(origGraph); }
 
     bool runQuickBB(int MaxTimeInSec, Timer *tim = NULL, bool sixtyFourBit = true);
+    // addition: in-process greedy min-fill elimination ordering of L(G), written in QuickBB's output format so that
+    // LGContract() consumes it unchanged.  Removes the system("quickbb_64 ...") boundary and its wall-clock cap
+    // (19.8 s of 21.2 s for qft8 in the reference) at the price of a (usually slightly) wider
+    // decomposition than QuickBB's branch-and-bound can reach.  Returns the width of the elimination order.
+    // `trials` > 1 repeats the greedy search with random tie-breaking (seeded) and keeps the cheapest order
+    // (smallest sum over eliminations of 4^(clique size), the contraction cost it implies).
+    int runMinFill(int trials = 16, unsigned seed = 12345);
     void Reset(std::shared_ptr<Network> inpNetwork = nullptr) {
         if (inpNetwork == nullptr) { origNetwork->Reset(); return; }
         Build(inpNetwork);
@@ -99,6 +108,73 @@ inline bool LineGraph::runQuickBB(int MaxTimeInSec, Timer *tim, bool sixtyFourBi
     std::cout << "===== End of QuickBB output =====" << std::endl << std::endl;
     if (tim) std::cout << "Time elapsed after outputting line graph and running QuickBB: { " << tim->getElapsed() << " }\n";
     return true;
+}
+
+inline int LineGraph::runMinFill(int trials, unsigned seed) {
+    const int n = static_cast<int>(GraphWires.size());
+    std::vector<std::vector<int>> adj0(n);
+    auto connectedIn = [](const std::vector<std::vector<int>> &adj, int a, int b) {
+        return std::find(adj[a].begin(), adj[a].end(), b) != adj[a].end();
+    };
+    for (const auto &e : LGEdges) {
+        const int a = e[0]->GetWireID(), b = e[1]->GetWireID();
+        if (a != b && !connectedIn(adj0, a, b)) { adj0[a].push_back(b); adj0[b].push_back(a); }
+    }
+    std::mt19937 rng(seed);
+    std::vector<int> bestOrder;
+    int bestWidth = 0;
+    double bestCost = -1.0;
+    if (n > 0) trials = std::min(trials, std::max(1, 16000 / n));       // keep large line graphs (GHZ-1000: 3000 wires) quick
+    for (int trial = 0; trial < std::max(1, trials); ++trial) {
+        std::vector<std::vector<int>> adj = adj0;
+        std::vector<bool> gone(n, false);
+        std::vector<long> fill(n, -1);                 // cached fill-in counts, -1 = stale
+        std::vector<int> order;
+        order.reserve(n);
+        int width = 0;
+        double cost = 0.0;
+        for (int step = 0; step < n; ++step) {
+            int best = -1, ties = 0;
+            long bestFill = 0;
+            for (int v = 0; v < n; ++v) {
+                if (gone[v]) continue;
+                if (fill[v] < 0) {
+                    long f = 0;
+                    const std::vector<int> &nb = adj[v];
+                    for (size_t i = 0; i < nb.size(); ++i)
+                        for (size_t j = i + 1; j < nb.size(); ++j)
+                            if (!connectedIn(adj, nb[i], nb[j])) ++f;
+                    fill[v] = f;
+                }
+                const bool better = best < 0 || fill[v] < bestFill || (fill[v] == bestFill && adj[v].size() < adj[best].size());
+                const bool tie = best >= 0 && fill[v] == bestFill && adj[v].size() == adj[best].size();
+                if (better) { best = v; bestFill = fill[v]; ties = 1; }
+                else if (tie && trial > 0 && (rng() % static_cast<unsigned>(++ties)) == 0) best = v;     // reservoir pick among ties
+            }
+            const std::vector<int> nb = adj[best];
+            width = std::max(width, static_cast<int>(nb.size()));
+            cost += std::pow(4.0, static_cast<double>(nb.size()) + 1.0);
+            for (size_t i = 0; i < nb.size(); ++i)
+                for (size_t j = i + 1; j < nb.size(); ++j)
+                    if (!connectedIn(adj, nb[i], nb[j])) { adj[nb[i]].push_back(nb[j]); adj[nb[j]].push_back(nb[i]); }
+            for (int u : nb) {
+                adj[u].erase(std::find(adj[u].begin(), adj[u].end(), best));
+                fill[u] = -1;
+                for (int w : adj[u]) fill[w] = -1;          // their neighbourhoods may have gained edges
+            }
+            adj[best].clear();
+            gone[best] = true;
+            order.push_back(best);
+        }
+        if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestWidth = width; bestOrder = order; }
+    }
+    mkdir("output", 0755);
+    std::ofstream out(qbbOutName);
+    out << " The treewidth of the graph in the file " << cnfName << " is " << bestWidth << " (greedy min-fill, in-process)" << std::endl;
+    out << " The optimal ordering is " << std::endl;
+    for (int v : bestOrder) out << v + 1 << " ";
+    out << std::endl;
+    return bestWidth;
 }
 
 inline bool LineGraph::LGContract() {

@@ -139,3 +139,17 @@ def test_reference_test_suite_drop_in(built, tmp_path):
     assert "TOTAL TEST FAILURE COUNT: 0." in log, log[-3000:]
     assert sum(1 for l in lines if l.strip() == "Passed") == 13 and not any(l.strip() == "Failed" for l in lines), log[-3000:]
     assert p.returncode == 0, p.stdout[-2000:]
+
+
+@pytest.mark.parametrize("name", ["qft8_X8", "testJW_YXXY", "qaoa20_node1_m125", "rand20_cn3_d12_zeros", "ghz64_zeros", "qaoa30_z27z29"])
+def test_in_process_minfill_ordering_gives_the_reference_value(built, name, tmp_path):
+    """SURVEY 8f-3: LineGraph::runMinFill() replaces the external quickbb_64 call; a different (here cheaper) plan,
+    the same value"""
+    rec = NETS[name]
+    cwd, qasm, meas, _ = golden_paths(rec)
+    out = qt.run_harness(["minfill", qasm, meas, os.path.join(str(tmp_path), "mf.qbb.out"), rec["reduce"]], cwd=cwd, timeout=600)
+    assert int(out["ok"][0]) == 1
+    val = complex(float(out["value"][0]), float(out["value"][1]))
+    assert _close(val, rec["value"]), (val, rec["value"])
+    if name == "qaoa30_z27z29":
+        assert int(out["flops"][0]) < rec["flops"]          # 2.2e10 vs QuickBB's 6.9e10 units
