@@ -4,6 +4,7 @@
 // files, ReduceCircuit, contract along a frozen QuickBB ordering or a recorded plan, read the value --
 // without paying process start-up and CUDA initialisation per call.  Same flow as qtorch's main.cpp
 // (/root/reference/src/main.cpp:74-198).
+#include <unistd.h>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -104,7 +105,14 @@ int qth_export_plan_linegraph(const char *qasm, const char *measure, const char 
         }
         if (reduce) net->ReduceCircuit();
         LineGraph lg(net);
-        lg.SetQBBOutFiles("/dev/null", qbbOut, "/dev/null");
+        if (qbbOut && qbbOut[0]) {
+            lg.SetQBBOutFiles("/dev/null", qbbOut, "/dev/null");
+        } else {
+            // no frozen QuickBB file: in-process min-fill ordering (LineGraph::runMinFill)
+            const std::string tmp = "/tmp/qtb_minfill_" + std::to_string(static_cast<long>(getpid())) + ".out";
+            lg.SetQBBOutFiles("/dev/null", tmp, "/dev/null");
+            lg.runMinFill();
+        }
         if (!lg.LGContract()) rc = 2;
         for (const auto &r : net->GetPlan()) {
             qtb_plan_step s;
