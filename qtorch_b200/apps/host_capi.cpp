@@ -188,4 +188,15 @@ int qth_qaoa_circuit_text(void *h, int edge, const double *betasGammas, int n, c
     return static_cast<int>(t.size());
 }
 
+// final cut string for given angles; bits[] receives numQubits 0/1 values; returns the number of qubits or -1
+int qth_maxcut_final_string(const char *graphFile, int p, const double *betasGammas, const char *outFile, int *bits, int maxBits, unsigned seed,
+                            double *probability) {
+    try {
+        std::vector<double> bg(betasGammas, betasGammas + 2 * p);
+        const std::vector<bool> ans = maxcutGetFinalString(graphFile, p, {}, bg, outFile, seed, probability);
+        for (size_t i = 0; i < ans.size() && static_cast<int>(i) < maxBits; i++) bits[i] = ans[i] ? 1 : 0;
+        return static_cast<int>(ans.size());
+    } catch (std::exception &e) { g_err = e.what(); return -1; } catch (const char *m) { g_err = m; return -1; }
+}
+
 }  // extern "C"

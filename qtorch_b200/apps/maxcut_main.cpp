@@ -6,7 +6,8 @@
 //    scope here, so a small derivative-free Nelder-Mead ascent with an evaluation cap takes its place.  Same start
 //    point (beta = 0.392699, gamma = 0.785399, maxcut.cpp:155-157); the angle file is rewritten after every
 //    evaluation like the reference does (maxcut.cpp:199-202).
-//  * Modes 1 and 2 (final bit-string sampler, maxcut.cpp:29-140) are not provided.
+//  * Modes 1 and 2 add the final bit-string sampler (maxcut.cpp:29-140): the n-qubit circuit is planned once with the
+//    in-process min-fill ordering and the n conditional probabilities re-use one compiled device plan.
 #include <sys/stat.h>
 #include <algorithm>
 #include <cstdlib>
@@ -69,13 +70,21 @@ int main(int argc, char *argv[]) {
         return -1;
     }
     const int p = atoi(argv[2]), mode = atoi(argv[3]);
-    if (mode != 0) {
-        std::cout << "Only mode 0 (optimal angles) is provided by the B200 build; the final-string sampler is not." << std::endl;
-        return -1;
-    }
-    const std::string outputPath(argv[4]);
-    const int maxEvals = argc > 5 ? atoi(argv[5]) : 200;
     mkdir("output", 0755);
+    if (mode == 1) {
+        // <graph> <p> 1 <input angle file> <output answer file>: final cut string for given angles (maxcut.cpp:258-287)
+        if (argc < 6) { std::cout << "Not enough arguments" << std::endl; return -1; }
+        try {
+            std::ifstream inAngles(argv[4]);
+            std::vector<double> bg;
+            for (int i = 0; i < 2 * p; ++i) { double z = 0.0; inAngles >> z; bg.push_back(z); }
+            maxcutGetFinalString(argv[1], p, {}, bg, argv[5]);
+        } catch (std::exception &e) { std::cout << e.what() << std::endl; return -1; } catch (const char *m) { std::cout << m << std::endl; return -1; }
+        return 0;
+    }
+    if (mode != 0 && mode != 2) { std::cout << "mode must be 0, 1 or 2" << std::endl; return -1; }
+    const std::string outputPath(mode == 2 ? "tempAngles.txt" : argv[4]);
+    const int maxEvals = (mode == 0 && argc > 5) ? atoi(argv[5]) : 200;
     try {
         Timer clock;
         clock.start();
@@ -106,6 +115,10 @@ int main(int argc, char *argv[]) {
         std::cout << "F_p(start) evaluations: " << evals << ", best F_p = " << bestSeen << std::endl;
         std::cout << "Terms per second: " << evals * static_cast<double>(data.pairs.size()) / seconds << std::endl;
         std::cout << "Took " << clock.getElapsed() << " seconds" << std::endl;
+        if (mode == 2) {                      // angles, then the final string with them (maxcut.cpp:293-324)
+            std::remove("tempAngles.txt");
+            maxcutGetFinalString(argv[1], p, {}, best, argv[4]);
+        }
     } catch (std::exception &e) {
         std::cout << e.what() << std::endl;
         return -1;

@@ -11,7 +11,9 @@
 #pragma once
 
 #include <fstream>
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <functional>
 #include <iostream>
 #include <sstream>
@@ -304,5 +306,100 @@ private:
     std::vector<Term> mTerms;
     long long mEvaluations{0};
 };
+
+// ----------------------------------------------------------------------------------------------------------------
+// Final cut string (counterpart of maxcutGetFinalString, /root/reference/src/maxcut.cpp:29-140): qubit by qubit, the
+// probability of reading 0 given the bits chosen so far decides the next bit.  The reference re-parses and re-plans
+// the full n-qubit circuit n times; here the circuit is planned ONCE (the plan does not depend on the measurement
+// caps), compiled to one device plan, and the n evaluations only swap the rank-1 cap tensors.
+// `contractionSequence`: a recorded plan in mCreatedFrom numbering (as produced by preProcess); empty -> in-process
+// min-fill line-graph plan on the reduced circuit.
+inline std::vector<bool> maxcutGetFinalString(const std::string &graphFilePath, int p, const std::vector<std::pair<int, int>> &contractionSequence,
+                                              const std::vector<double> &gAndB, const std::string &outfilePath, unsigned tieSeed = 0,
+                                              double *stringProbability = nullptr) {
+    Timer clock;
+    clock.start();
+    ExtraData data(p, graphFilePath.c_str());
+    const int n = data.numQubits;
+    std::ostringstream circuit;
+    circuit << n << std::endl;
+    outputInitialPlusStateToFile(circuit, n);
+    applyU_CsThenU_Bs(data.pairs, p, gAndB, n, circuit);
+    std::string allTrace;
+    for (int q = 0; q < n; ++q) allTrace += "T ";
+
+    // plan on the host (no arithmetic), inputs snapshot in id order
+    const bool before = device::Engine::PlanOnly();
+    device::Engine::SetPlanOnly(true);
+    std::vector<std::vector<std::complex<double>>> inputs;
+    std::vector<qtb_plan_step> steps;
+    long long units = 0;
+    try {
+        std::istringstream text(circuit.str());
+        std::shared_ptr<Network> net = std::make_shared<Network>(text, allTrace);
+        for (int i = 0; i < net->GetNumOriginalNodes(); ++i) inputs.push_back(net->GetAllNodes()[i]->GetTensorVals());
+        if (contractionSequence.empty()) {
+            net->ReduceCircuit();
+            LineGraph lg(net);
+            const std::string tmp = "/tmp/qtb_finalstring_" + std::to_string(reinterpret_cast<uintptr_t>(net.get())) + ".out";
+            lg.SetQBBOutFiles("/dev/null", tmp, "/dev/null");
+            lg.runMinFill();
+            lg.LGContract();
+            std::remove(tmp.c_str());
+        } else {
+            ContractionTools tools(net);
+            tools.ContractGivenSequence(contractionSequence);
+        }
+        units = net->getNumFloatOps();
+        for (const auto &r : net->GetPlan()) {
+            qtb_plan_step st;
+            std::memset(&st, 0, sizeof(st));
+            st.a = r.a; st.b = r.b; st.k = static_cast<int>(r.posA.size());
+            for (int j = 0; j < st.k; ++j) { st.pos_a[j] = static_cast<int8_t>(r.posA[j]); st.pos_b[j] = static_cast<int8_t>(r.posB[j]); }
+            steps.push_back(st);
+        }
+    } catch (...) {
+        device::Engine::SetPlanOnly(before);
+        throw;
+    }
+    device::Engine::SetPlanOnly(before);
+
+    std::vector<int> ranks;
+    for (const auto &in : inputs) { int r = 0; while ((static_cast<size_t>(1) << (2 * r)) < in.size()) ++r; ranks.push_back(r); }
+    qtb_ctx *ctx = device::Engine::Get().ctx();
+    qtb_plan *plan = nullptr;
+    device::check(qtb_plan_create(ctx, static_cast<int>(ranks.size()), ranks.data(), static_cast<int>(steps.size()), steps.data(), &plan));
+
+    const size_t firstCap = inputs.size() - static_cast<size_t>(n);        // the n measurement caps are the last original nodes
+    const std::vector<std::complex<double>> capTrace = TraceNode().GetTensorVals(), capZero = ProjectZero().GetTensorVals(),
+                                            capOne = ProjectOne().GetTensorVals();
+    std::vector<bool> answer;
+    std::mt19937 coin(tieSeed ? tieSeed : static_cast<unsigned>(std::time(nullptr)));
+    double currentProb = 1.0;
+    for (int q = 0; q < n; ++q) {
+        for (int j = 0; j < n; ++j)
+            inputs[firstCap + j] = j < static_cast<int>(answer.size()) ? (answer[j] ? capOne : capZero) : (j == q ? capZero : capTrace);
+        std::vector<const double *> ptrs;
+        for (const auto &in : inputs) ptrs.push_back(reinterpret_cast<const double *>(in.data()));
+        double out[2] = {0.0, 0.0};
+        device::check(qtb_plan_run_host(ctx, plan, ptrs.data(), out));
+        const double probZero = out[0] / currentProb;                       // P(bit q = 0 | bits so far)
+        if (probZero > 0.5) { currentProb *= probZero; answer.push_back(false); }
+        else if (probZero < 0.5) { currentProb *= (1.0 - probZero); answer.push_back(true); }
+        else { answer.push_back((coin() & 1u) != 0); currentProb *= 0.5; }
+    }
+    qtb_plan_destroy(ctx, plan);
+    if (stringProbability) *stringProbability = currentProb;      // probability of the whole string (product of the conditionals)
+
+    int cut = 0;
+    for (const auto &e : data.pairs) if (answer[e.first] != answer[e.second]) ++cut;
+    std::ofstream result(outfilePath);
+    result << data.fileName << std::endl;
+    for (bool b : answer) result << b << " ";
+    result << std::endl << "Cut edges: " << cut << "/" << data.numQubits * 3 / 2 << std::endl;
+    result << "Time elapsed: " << clock.getElapsed() << std::endl;
+    if (!detail::quietMode()) std::cout << "Final string contracted with " << units << " units per qubit; cut edges: " << cut << std::endl;
+    return answer;
+}
 
 }  // namespace qtorch

@@ -38,6 +38,7 @@ def host_library():
         H.qth_contract_sequence.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ctypes.c_int, cd, cll, ci, cd]
         H.qth_export_plan_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_QthPlan)]
         H.qth_maxcut_circuit_text.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, cd, ctypes.c_char_p, ctypes.c_int, ci, ci]
+        H.qth_maxcut_final_string.argtypes = [ctypes.c_char_p, ctypes.c_int, cd, ctypes.c_char_p, ci, ctypes.c_int, ctypes.c_uint, cd]
         H.qth_qaoa_create.restype = ctypes.c_void_p
         H.qth_qaoa_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         H.qth_qaoa_destroy.argtypes = [ctypes.c_void_p]
@@ -62,6 +63,18 @@ def maxcut_circuit_text(graph_file, p, edge, betas_gammas):
     if n < 0:
         _raise(H, n)
     return buf.value.decode(), ne.value, nq.value
+
+
+def maxcut_final_string(graph_file, p, betas_gammas, out_file, seed=1):
+    """final cut string for the given angles (counterpart of the reference's maxcutGetFinalString)"""
+    H = host_library()
+    bg = (ctypes.c_double * len(betas_gammas))(*betas_gammas)
+    bits = (ctypes.c_int * 4096)()
+    prob = ctypes.c_double()
+    n = H.qth_maxcut_final_string(graph_file.encode(), p, bg, out_file.encode(), bits, 4096, seed, ctypes.byref(prob))
+    if n < 0:
+        _raise(H, n)
+    return [bits[i] for i in range(n)], prob.value
 
 
 class QaoaObjective:

@@ -73,3 +73,34 @@ def test_qaoa_sharding_over_ranks_sums_to_the_serial_objective(built):
         q.close()
     assert sorted(seen) == list(range(len(rec["terms"])))
     assert abs(total - rec["fp"]) <= 1e-10 * rec["fp"]
+
+
+@pytest.mark.gpu
+def test_final_string_probability_matches_reference(built, tmp_path):
+    """maxcutGetFinalString (reference maxcut.cpp:29-140): the product of the n conditional probabilities must equal the
+    probability of the chosen bit string, which the UNMODIFIED reference computes by contracting the full 30-qubit
+    circuit with every qubit projected (ref_harness `stoch`)."""
+    from oracle import oracle as O
+    if not O.ref_available():
+        pytest.skip("oracle/_ref not built")
+    graph = os.path.join(GOLDEN, "Samples", "3regRand30Node50.dgf")
+    bg = [0.392699, 0.785399]
+    out = os.path.join(str(tmp_path), "answer.txt")
+    bits, prob = host_api.maxcut_final_string(graph, 1, bg, out, seed=7)
+    assert len(bits) == 30 and prob > 0
+    lines = open(out).read().splitlines()
+    assert lines[0] == graph and lines[1].split() == [str(b) for b in bits] and lines[2].startswith("Cut edges: ") and lines[2].endswith("/45")
+    cut = sum(1 for l in open(graph) if l.startswith("e") and bits[int(l.split()[1])] != bits[int(l.split()[2])])
+    assert lines[2] == "Cut edges: %d/45" % cut and cut >= 23          # greedy sampling of a p=1 QAOA state beats a random cut on average
+    # the same circuit text the reference would write (all 45 edges, maxcut.cpp:53-57), every qubit projected on its bit
+    edges = [tuple(int(x) for x in l.split()[1:]) for l in open(graph) if l.startswith("e")]
+    qasm = ["30"] + ["H %d" % q for q in range(30)]
+    for a, b in edges:
+        qasm += ["CNOT %d %d" % (a, b), "Rz -0.785399 %d" % b, "CNOT %d %d" % (a, b)]
+    qasm += ["Rx 0.785398 %d" % q for q in range(30)]
+    qf, mf = os.path.join(str(tmp_path), "full.qasm"), os.path.join(str(tmp_path), "full.meas")
+    open(qf, "w").write("\n".join(qasm) + "\n")
+    open(mf, "w").write(" ".join(str(b) for b in bits) + "\n")
+    ref = O.ref_harness(["stoch", qf, mf, 8], timeout=900)
+    pref = float(ref["value"][0])
+    assert abs(prob - pref) <= 1e-10 * max(1.0, abs(pref)) and abs(prob - pref) <= 1e-6 * pref, (prob, pref)
