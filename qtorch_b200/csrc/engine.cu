@@ -376,7 +376,6 @@ static int launch_reduce(qtb_ctx *ctx, const StepGeom &g, const double2 *A, cons
     }
     const unsigned grid = std::min<unsigned>(p.nTiles, std::min<unsigned>(REDUCE_MAX_BLOCKS, (unsigned)ctx->numSMs * 8));
     switch (g.rC) {
-        case 0: k_reduce<1><<<grid, 256, 0, s>>>(p); k_reduce_final<1><<<1, 32, 0, s>>>(p.partial, C, grid); break;
         case 1: k_reduce<4><<<grid, 256, 0, s>>>(p); k_reduce_final<4><<<1, 128, 0, s>>>(p.partial, C, grid); break;
         default: k_reduce<16><<<grid, 256, 0, s>>>(p); k_reduce_final<16><<<1, 512, 0, s>>>(p.partial, C, grid); break;
     }
@@ -463,7 +462,6 @@ static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std:
     return off;
 }
 
-// copy-step aware micro kernel wrapper lives in kernels.cuh (k_micro handles KIND_COPY)
 
 static int ring_reserve(qtb_ctx *ctx, size_t bytes, size_t &off) {
     bytes = (bytes + 255) & ~(size_t)255;

@@ -8,15 +8,17 @@
 // (the operand with the larger free dimension), so D is C or C^T; every operand and the output are
 // addressed through per-bit shift tables, so any leg placement is legal.
 //
-// Structure (one persistent CTA per SM: 8 math warps + 1 producer warp, mbarrier full/empty ring):
-//   * tile gather  : 16-byte cp.async.cg (LDGSTS) per element, lanes ordered along the operand's
-//                    memory-contiguous bits (host-computed bit permutation) -> >= 64 B runs always
-//   * pipeline     : STAGES-deep ring over the FLAT (tile, k-chunk) sequence, so the next tile's
-//                    operands stream in while the current tile's DMMAs and C stores are in flight
-//   * math         : mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- tcgen05 has no f64 kind; this
-//                    is the B200 FP64 tensor pipe, 37.1 TFLOP/s measured), complex product as
-//                    4 real DMMAs (Xr*Yr, -Xi*Yi, Xr*Yi, Xi*Yr); fragments come out of shared
-//                    memory as one conflict-free LDS.128 (re, im) per lane
+// Structure (one persistent CTA per SM: 16 or 8 math warps + a producer warpgroup, mbarrier full/empty ring):
+//   * tile gather  : the producer warpgroup issues 16-byte cp.async.cg (LDGSTS) per element, lanes ordered along the
+//                    operand's memory-contiguous bits (host-computed bit permutation) -> >= 64 B runs always; the
+//                    dimension that is contiguous in HBM is also contiguous in shared memory, so both halves of a
+//                    32-byte sector are served by one request
+//   * pipeline     : STAGES-deep ring over the FLAT (tile, k-chunk) sequence, so the next tile's operands stream in
+//                    while the current tile's DMMAs and C stores are in flight; cp.async.mbarrier.arrive.noinc signals
+//                    "full", one arrive per math warp signals "empty"; setmaxnreg shifts registers to the math warps
+//   * math         : mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- tcgen05 has no f64 kind; this is the B200 FP64
+//                    tensor pipe, 37.1 TFLOP/s measured); complex product as 4 real DMMAs (4M) or 3 (3M, Karatsuba);
+//                    fragments come out of shared memory as one conflict-free LDS.128 (re, im) per lane
 //   * epilogue     : accumulators -> C directly, 128-byte runs per row group
 #pragma once
 #include <cuda_runtime.h>
