@@ -329,7 +329,8 @@ def main():
         terms = K * world
         value = terms / (ms_dev * 1e-3)
         e2e = terms / (ms_e2e * 1e-3)
-        # roofline of the dominant kernel: the DMMA tile kernel on the four rank-14 steps (kernel code 2)
+        # roofline of the dominant kernel: the DMMA tile kernel on the rank-14 steps (trace code 2; the fourth rank-14 step
+        # runs fused with the closing inner product, code 6, and is left out of this average)
         gett = [r for r in trace if r["kernel"] == 2 and max(r["rank_a"], r["rank_b"]) >= 9 and r["k"] == 3 and r["rank_a"] + r["rank_b"] - 6 == 14]
         total_ms = sum(r["ms"] for r in trace) or 1.0
         roof = None
@@ -345,7 +346,7 @@ def main():
                     # achieved counts the ALGORITHMIC 8 flops per complex MAC; the 3M kernel issues 6 on the tensor pipe
                     "tensor_pipe_flops_per_unit": 6 if three_m else 8, "tensor_pipe_frac": ach * (0.75 if three_m else 1.0) / FP64_PEAK_TFLOPS,
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_summary.txt); algorithmic 4.33e9
-                    "traffic": 4.50e9, "launches_timed": len(gett), "avg_ms": avg_ms,
+                    "traffic": 4.42e9, "launches_timed": len(gett), "avg_ms": avg_ms,
                     "share_of_step": sum(r["ms"] for r in gett) / total_ms,
                     "peak_source": "measured: tools/probe_fp64 DMMA m8n8k4 on this pool's B200 (profiles/r01_probe_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry"}
         by_kind = {}

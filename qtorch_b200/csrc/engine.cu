@@ -51,7 +51,7 @@ struct GettChoice { int cfg; bool swap; };      // cfg: 0 C1/TK16 1 C1/TK4 2 C2/
 typedef void (*GettKernel)(const GettParams);
 struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; };
 // C1: 128x64 tile, compute-bound big x big;  C2: 256x16;  C3: 256x8 (N <= 4 padded) -- streaming
-static GettInst g_gett[9] = {
+static GettInst g_gett[11] = {
     {k_gett<4, 2, 4, 4, 16, 3>, 128, 64, 16, GettCfg<4, 2, 4, 4, 16, 3>::NT, GettCfg<4, 2, 4, 4, 16, 3>::SMEM, 1},
     {k_gett<4, 2, 4, 4, 4, 12>, 128, 64, 4, GettCfg<4, 2, 4, 4, 4, 12>::NT, GettCfg<4, 2, 4, 4, 4, 12>::SMEM, 1},
     {k_gett<8, 1, 4, 2, 16, 2>, 256, 16, 16, GettCfg<8, 1, 4, 2, 16, 2>::NT, GettCfg<8, 1, 4, 2, 16, 2>::SMEM, 1},
@@ -64,7 +64,16 @@ static GettInst g_gett[9] = {
     {k_gett<4, 4, 2, 2, 16, 5, 1>, 64, 64, 16, GettCfg<4, 4, 2, 2, 16, 5, 1>::NT, GettCfg<4, 4, 2, 2, 16, 5, 1>::SMEM, 1},
     // C1 "3M", 8 math warps of 32x16 (more registers per warp: double-buffered fragments)
     {k_gett<2, 4, 4, 2, 16, 5, 1>, 64, 64, 16, GettCfg<2, 4, 4, 2, 16, 5, 1>::NT, GettCfg<2, 4, 4, 2, 16, 5, 1>::SMEM, 1},
+    // fused with the inner product that follows (FUSE = 1): variants of 6 (4M) and 7 (3M)
+    {k_gett<4, 4, 4, 2, 16, 3, 0, 1>, 128, 64, 16, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::NT, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::SMEM, 1},
+    {k_gett<4, 4, 2, 2, 16, 5, 1, 1>, 64, 64, 16, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::NT, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::SMEM, 1},
 };
+static int fused_variant_of(int cfg) { return cfg == 6 ? 9 : cfg == 7 ? 10 : -1; }
+static bool fusion_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_FUSE_DOT"); v = (e && !atoi(e)) ? 0 : 1; }
+    return v == 1;
+}
 static int c1_variant() {
     static int v = -1;
     // 2 = "3M" complex product, 16 math warps (default);  3 = 3M, 8 math warps;  1 = 4M, 16 math warps;  0 = 4M, 8 math warps
@@ -203,6 +212,29 @@ static void build_reduce(const StepGeom &g, const double2 *A, const double2 *B, 
     }
 }
 
+// A DMMA step whose result T is immediately contracted with another tensor D over ALL of T's legs (an inner product,
+// rC = 0) can run fused: the tile kernel multiplies its accumulators with the matching D elements instead of storing T.
+// `tIsA`: T is operand A of the inner product.  Returns false if the pair does not qualify.
+static bool fusable_pair(const StepGeom &g1, int kind1, const GettChoice &gc1, const StepGeom &g2, bool tIsA) {
+    if (!fusion_enabled() || kind1 != KIND_GETT || fused_variant_of(gc1.cfg) < 0) return false;
+    if (g2.rC != 0 || g2.k != g1.rC || g2.rA != g2.rB || g2.rA != g1.rC) return false;
+    (void)tIsA;
+    return true;
+}
+// shDx / shDy of the fused kernel: where each x / y bit of the tile kernel lands inside D's element index
+static void add_fusion(const StepGeom &g2, bool tIsA, const double2 *D, double2 *partial, GettParams &p) {
+    // leg l of T pairs with leg dLeg[l] of D
+    int dLeg[QTB_MAXR];
+    for (int j = 0; j < g2.k; j++) {
+        if (tIsA) dLeg[g2.posA[j]] = g2.posB[j];
+        else dLeg[g2.posB[j]] = g2.posA[j];
+    }
+    for (int j = 0; j < p.xbits; j++) p.shDx[j] = (uint8_t)(2 * dLeg[p.shCx[j] / 2] + (p.shCx[j] & 1));
+    for (int j = 0; j < p.ybits; j++) p.shDy[j] = (uint8_t)(2 * dLeg[p.shCy[j] / 2] + (p.shCy[j] & 1));
+    p.dotD = D;
+    p.dotPartial = partial;
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-rank pooled device memory
 struct Pool {
@@ -330,6 +362,9 @@ struct qtb_ctx_s {
     std::vector<TraceRec> traceRecs;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     int microLog4 = MICRO_DEFAULT_LOG4;
+    // a big DMMA step that has been requested but not launched yet: if the very next step is the inner product of its
+    // result with another tensor, both run as one fused kernel (the intermediate never touches HBM)
+    struct Held { bool active = false; StepGeom g; GettChoice gc{0, false}; const double2 *A = nullptr, *B = nullptr; double2 *C = nullptr; } held;
     double *batchOut = nullptr; size_t batchOutCap = 0;      // pinned gather buffer of qtb_plans_run_batched
     // NCCL
     void *comm = nullptr; int nRanks = 1, rank = 0;
@@ -476,7 +511,21 @@ static int ring_reserve(qtb_ctx *ctx, size_t bytes, size_t &off) {
     return QTB_OK;
 }
 
+static int enqueue_big(qtb_ctx *ctx, const StepGeom &g, int kind, const GettChoice &gc, const double2 *A, const double2 *B,
+                       double2 *C, cudaStream_t s);
+
+static int launch_held_locked(qtb_ctx *ctx) {
+    if (!ctx->held.active) return QTB_OK;
+    ctx->held.active = false;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
+    ST(enqueue_big(ctx, ctx->held.g, KIND_GETT, ctx->held.gc, ctx->held.A, ctx->held.B, ctx->held.C, ctx->stream));
+    if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, ctx->held.g.rA, ctx->held.g.rB, ctx->held.g.k, KIND_GETT}); }
+    return QTB_OK;
+}
+
 static int flush_locked(qtb_ctx *ctx) {
+    ST(launch_held_locked(ctx));          // program order: the held step was requested before anything still pending
     if (ctx->pending.empty() && ctx->pendingUploads.empty()) {
         for (auto &f : ctx->deferredFrees) ctx->pool.release(f.first, f.second);
         ctx->deferredFrees.clear();
@@ -512,6 +561,23 @@ static int ensure_buffer(qtb_ctx *ctx, qtb_tensor t) {
     void *p = nullptr;
     ST(ctx->pool.alloc(t->rank, &p));
     t->d = (double2 *)p; t->pooled = true;
+    return QTB_OK;
+}
+
+// fused DMMA step + inner product: T = contract(A1, B1) is never materialised; out = <T, D>
+static int enqueue_fused(qtb_ctx *ctx, const StepGeom &g1, const GettChoice &gc1, const double2 *A1, const double2 *B1,
+                         const StepGeom &g2, bool tIsA, const double2 *D, double2 *out, cudaStream_t s) {
+    GettParams p;
+    build_gett(g1, gc1, A1, B1, nullptr, p);
+    add_fusion(g2, tIsA, D, ctx->reduceScratch, p);
+    const int cfg = fused_variant_of(gc1.cfg);
+    const GettInst &inst = g_gett[cfg];
+    const unsigned nTiles = p.nTilesX * p.nTilesY;
+    const unsigned grid = std::min<unsigned>(nTiles, (unsigned)(ctx->numSMs * inst.occ));
+    inst.fn<<<grid, inst.NT, inst.smem, s>>>(p);
+    k_reduce_final<1><<<1, 32, 0, s>>>(ctx->reduceScratch, out, grid);
+    CU(cudaGetLastError());
+    ctx->stats.launches += 2;
     return QTB_OK;
 }
 
@@ -637,7 +703,7 @@ int qtb_tensor_free(qtb_ctx *ctx, qtb_tensor t) {
     if (t->d && t->pooled) {
         // stream-ordered: deferred micro-steps may still reference the buffer, so it returns to the
         // pool right after the next flush is enqueued
-        if (ctx->pending.empty() && ctx->pendingUploads.empty()) ctx->pool.release(t->rank, t->d);
+        if (ctx->pending.empty() && ctx->pendingUploads.empty() && !ctx->held.active) ctx->pool.release(t->rank, t->d);
         else ctx->deferredFrees.push_back({t->rank, (void *)t->d});
     }
     delete t;
@@ -722,12 +788,30 @@ int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos
         ctx->pending.push_back(ps);
         ctx->producedLevel[c->d] = lvl;
         if (ctx->pending.size() >= 8192) ST(flush_locked(ctx));
-    } else {
-        ST(flush_locked(ctx));
+    } else if (ctx->held.active && kind == KIND_REDUCE && (a->d == ctx->held.C || b->d == ctx->held.C) &&
+               fusable_pair(ctx->held.g, KIND_GETT, ctx->held.gc, g, a->d == ctx->held.C)) {
+        // the held DMMA step and this inner product run as ONE kernel; the intermediate is never materialised
+        const bool tIsA = a->d == ctx->held.C;
+        const qtb_ctx_s::Held h = ctx->held;
+        ctx->held.active = false;
+        ST(flush_locked(ctx));                                    // deferred micro-steps requested in between go first
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
-        ST(enqueue_big(ctx, g, kind, gc, a->d, b->d, c->d, ctx->stream));
-        if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, g.rA, g.rB, g.k, kind}); }
+        ST(enqueue_fused(ctx, h.g, h.gc, h.A, h.B, g, tIsA, tIsA ? b->d : a->d, c->d, ctx->stream));
+        if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, h.g.rA, h.g.rB, h.g.k, KIND_FUSED}); }
+        for (auto &f : ctx->deferredFrees) ctx->pool.release(f.first, f.second);
+        ctx->deferredFrees.clear();
+    } else {
+        ST(flush_locked(ctx));
+        if (kind == KIND_GETT && fusion_enabled() && fused_variant_of(gc.cfg) >= 0 && g.rC >= 10) {
+            // hold it back until the next request shows whether it can be fused (launched by the next flush at the latest)
+            ctx->held.active = true; ctx->held.g = g; ctx->held.gc = gc; ctx->held.A = a->d; ctx->held.B = b->d; ctx->held.C = c->d;
+        } else {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
+            ST(enqueue_big(ctx, g, kind, gc, a->d, b->d, c->d, ctx->stream));
+            if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, g.rA, g.rB, g.k, kind}); }
+        }
     }
     c->hasData = true;
     return QTB_OK;

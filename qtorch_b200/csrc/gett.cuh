@@ -44,6 +44,12 @@ struct GettParams {
     // LDGSTS sector request serves both lanes (otherwise every sector is requested twice).  Both layouts give
     // conflict-free LDS.128 fragment reads: [k][x] with row stride T+2, or [x][k] with row stride TK+4 (== 4 mod 8).
     uint16_t xsX, xsK, ysY, ysK;
+    // fused inner product (FUSE = 1 instantiations): instead of writing D, accumulate sum D[x,y] * dotD[perm(x,y)] --
+    // the step that follows contracts the result with `dotD` over ALL legs, so the 4^rC-element intermediate is never
+    // written to or re-read from HBM.  shDx/shDy: x / y bit j -> bit position inside dotD's element index.
+    const double2 *dotD;
+    double2 *dotPartial;              // one partial sum per CTA
+    uint8_t shDx[32], shDy[32];
 };
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, const double a, const double b) {
@@ -86,7 +92,7 @@ __device__ __forceinline__ uint32_t hitab_lookup(const HiTab &tab, uint32_t v, i
     return o;
 }
 
-template <int WX, int WY, int FX, int FY, int TK, int STAGES, int MODE3M = 0>
+template <int WX, int WY, int FX, int FY, int TK, int STAGES, int MODE3M = 0, int FUSE = 0>
 struct GettCfg {
     static constexpr int NW = WX * WY;                        // math warps; one more warpgroup (4 warps) produces
     static constexpr int NPT = 128;                           // producer threads
@@ -101,8 +107,8 @@ struct GettCfg {
     static constexpr int YS = (TK * LDY > TN * LDK) ? TK * LDY : TN * LDK;
     static constexpr int STAGE_ELEMS = XS + YS;
     static constexpr int XROUNDS = (TM * TK + NPT - 1) / NPT, YROUNDS = (TN * TK + NPT - 1) / NPT;
-    static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 2 * XROUNDS + 2 * YROUNDS;   // uint32 tables
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 16 + TAB * 4 + 2 * STAGES * 8 + 16 + 6 * sizeof(HiTab);
+    static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 2 * XROUNDS + 2 * YROUNDS + (FUSE ? TM + TN + 64 : 0);   // uint32 tables
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 16 + TAB * 4 + 2 * STAGES * 8 + 16 + 32 * FUSE + (6 + 2 * FUSE) * sizeof(HiTab);
 };
 
 __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
@@ -137,9 +143,9 @@ template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile
 // MODE3M = 1: the complex product uses three real DMMAs per tile pair instead of four (Karatsuba / "3M":
 //   T1 = Xr*Yr, T2 = Xi*Yi, T3 = (Xr+Xi)*(Yr+Yi);  Re = T1 - T2, Im = T3 - T1 - T2), 25 % less tensor-pipe work for
 // the same algorithmic 8*U flops, at the price of a third accumulator set.
-template <int WX, int WY, int FX, int FY, int TK, int STAGES, int MODE3M = 0>
+template <int WX, int WY, int FX, int FY, int TK, int STAGES, int MODE3M = 0, int FUSE = 0>
 __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams p) {
-    using Cfg = GettCfg<WX, WY, FX, FY, TK, STAGES, MODE3M>;
+    using Cfg = GettCfg<WX, WY, FX, FY, TK, STAGES, MODE3M, FUSE>;
     constexpr int NW = Cfg::NW, NT = Cfg::NT, TM = Cfg::TM, TN = Cfg::TN;
     const uint32_t xsX = p.xsX, xsK = p.xsK, ysY = p.ysY, ysK = p.ysK;
     constexpr int TMB = ilog2(TM), TNB = ilog2(TN), TKB = ilog2(TK);
@@ -150,7 +156,9 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
     uint32_t *tab = reinterpret_cast<uint32_t *>(smemRaw + (size_t)STAGES * Cfg::STAGE_ELEMS * 16);
     uint32_t *tXx = tab, *tCx = tXx + TM, *tYy = tCx + TM, *tCy = tYy + TN, *tXk = tCy + TN, *tYk = tXk + TK;
     uint32_t *dXo = tYk + TK, *dXs = dXo + XROUNDS, *dYo = dXs + XROUNDS, *dYs = dYo + YROUNDS;   // per-round deltas
-    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(dYs + YROUNDS) + 7) & ~(uintptr_t)7);
+    uint32_t *tDx = dYs + YROUNDS, *tDy = tDx + (FUSE ? TM : 0);                                   // fused dot: tile-local -> dotD offset
+    double2 *dotRed = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(tDy + (FUSE ? TN : 0)) + 15) & ~(uintptr_t)15);   // NW partials
+    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(FUSE ? (uint32_t *)(dotRed + NW) : dYs + YROUNDS) + 7) & ~(uintptr_t)7);
     HiTab *hi = reinterpret_cast<HiTab *>(bars + 2 * STAGES);     // [0] X by tile-x, [1] Y by tile-y, [2] X by chunk, [3] Y by chunk, [4] C by tile-x, [5] C by tile-y
     const uint32_t barBase = (uint32_t)__cvta_generic_to_shared(bars);        // full[s] = barBase + 8 s, empty[s] = full + 8 STAGES
 
@@ -179,6 +187,12 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
     hitab_build(hi[3], p.shYk, TKB, kHiBits, tid, NT);
     hitab_build(hi[4], p.shCx, TMB, xHiBits, tid, NT);
     hitab_build(hi[5], p.shCy, p.nyBits, yHiBits, tid, NT);
+    if (FUSE) {
+        hitab_build(hi[6], p.shDx, TMB, xHiBits, tid, NT);
+        hitab_build(hi[7], p.shDy, p.nyBits, yHiBits, tid, NT);
+        for (int i = tid; i < TM; i += NT) tDx[i] = scatter_bits(i, p.shDx, 0, TMB);
+        for (int i = tid; i < TN; i += NT) tDy[i] = (uint32_t)i < nyValid ? scatter_bits(i, p.shDy, 0, p.nyBits) : 0u;
+    }
     // zero the operand ring once: padded y columns (N < TN) are never written again
     for (int i = tid; i < STAGES * Cfg::STAGE_ELEMS; i += NT) stages[i] = make_double2(0.0, 0.0);
     if (tid == 0) {
@@ -265,6 +279,7 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
     const uint32_t xFrag0 = (wx0 + g) * xsX + t * xsK, yFrag0 = (wy0 + g) * ysY + t * ysK;     // this lane's fragment origin
     // 4M: accR = Re, accI = Im.   3M: accR = T1, accI = T2, acc3 = T3.
     double accR[FX][FY][2], accI[FX][FY][2], acc3[MODE3M ? FX : 1][MODE3M ? FY : 1][2];
+    double dotR = 0.0, dotI = 0.0;                      // FUSE: running sum D[x,y] * dotD[..] of this thread
     uint32_t ti = 0, ch = 0;
 #pragma unroll 1
     for (uint32_t q = 0; q < total; q++) {
@@ -357,6 +372,34 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
             const uint32_t tile = blockIdx.x + ti * gridDim.x;
             const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
             double2 *cb = p.C + hitab_lookup(hi[4], tx, xParts) + hitab_lookup(hi[5], ty, yParts);
+            const double2 *db = FUSE ? p.dotD + hitab_lookup(hi[6], tx, xParts) + hitab_lookup(hi[7], ty, yParts) : nullptr;
+            if (FUSE) {
+                // gather this lane's dotD elements first (all loads in flight together), then combine
+                double2 dv[FX][FY][2];
+#pragma unroll
+                for (int i = 0; i < FX; i++) {
+                    const uint32_t ox = tDx[wx0 + i * 8 + g];
+#pragma unroll
+                    for (int j = 0; j < FY; j++) {
+                        const int y0 = wy0 + j * 8 + 2 * t;
+                        dv[i][j][0] = (uint32_t)y0 < nyValid ? db[ox + tDy[y0]] : make_double2(0.0, 0.0);
+                        dv[i][j][1] = (uint32_t)(y0 + 1) < nyValid ? db[ox + tDy[y0 + 1]] : make_double2(0.0, 0.0);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < FX; i++)
+#pragma unroll
+                    for (int j = 0; j < FY; j++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            double re, im;
+                            if (MODE3M) { re = accR[i][j][h] - accI[i][j][h]; im = acc3[i][j][h] - accR[i][j][h] - accI[i][j][h]; }
+                            else { re = accR[i][j][h]; im = accI[i][j][h]; }
+                            dotR = fma(re, dv[i][j][h].x, dotR); dotR = fma(-im, dv[i][j][h].y, dotR);
+                            dotI = fma(re, dv[i][j][h].y, dotI); dotI = fma(im, dv[i][j][h].x, dotI);
+                        }
+            }
+            if (!FUSE) {
 #pragma unroll
             for (int i = 0; i < FX; i++) {
                 const uint32_t ox = tCx[wx0 + i * 8 + g];
@@ -374,9 +417,23 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
                     if ((uint32_t)(y0 + 1) < nyValid) cb[ox + tCy[y0 + 1]] = make_double2(re1, im1);
                 }
             }
+            }
             ch = 0; ++ti;
         } else {
             ++ch;
+        }
+    }
+    if (FUSE) {
+        // CTA partial of the fused inner product: shuffle tree per warp, then a named barrier over the math warps only
+        // (the producer warpgroup may already have exited)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { dotR += __shfl_xor_sync(0xffffffffu, dotR, o); dotI += __shfl_xor_sync(0xffffffffu, dotI, o); }
+        if (lane == 0) dotRed[warp] = make_double2(dotR, dotI);
+        asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");
+        if (tid == 0) {
+            double sr = 0.0, si = 0.0;
+            for (int w = 0; w < NW; w++) { sr += dotRed[w].x; si += dotRed[w].y; }
+            p.dotPartial[blockIdx.x] = make_double2(sr, si);
         }
     }
 }

@@ -8,6 +8,8 @@
 // launches each.
 
 struct PlanSeg {
+    bool fused = false;           // DMMA step + the inner product that follows, one kernel (g2 / tIsA / D describe the second step)
+    StepGeom g2; bool tIsA = false; const double2 *D = nullptr;
     bool micro = false;
     uint32_t microIndex = 0;      // index into segOffsetsDev
     int nSteps = 0;
@@ -45,12 +47,15 @@ static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s) {
             k_micro<<<1, QTB_MICRO_THREADS, QTB_MICRO_SMEM, s>>>(pl->microBlobDev, pl->segOffsetsDev + sg.microIndex);
             CU(cudaGetLastError());
             ctx->stats.launches++;
+        } else if (sg.fused) {
+            ST(enqueue_fused(ctx, sg.g, sg.gc, sg.A, sg.B, sg.g2, sg.tIsA, sg.D, sg.C, s));
         } else {
             ST(enqueue_big(ctx, sg.g, sg.kind, sg.gc, sg.A, sg.B, sg.C, s));
         }
         if (ctx->trace) {
             CU(cudaEventRecord(e1, s));
-            ctx->traceRecs.push_back({e0, e1, sg.micro ? 0 : sg.g.rA, sg.micro ? 0 : sg.g.rB, sg.micro ? sg.nSteps : sg.g.k, sg.micro ? KIND_MICRO : sg.kind});
+            ctx->traceRecs.push_back({e0, e1, sg.micro ? 0 : sg.g.rA, sg.micro ? 0 : sg.g.rB, sg.micro ? sg.nSteps : sg.g.k,
+                                      sg.micro ? KIND_MICRO : sg.fused ? KIND_FUSED : sg.kind});
         }
     }
     return QTB_OK;
@@ -127,10 +132,32 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
         const StepGeom &g = geoms[i];
         GettChoice gc{0, false};
         const int kind = choose_kind(g, gc, ctx->microLog4);
+        pl->units += (long long)g.units();
+        // fusion: this DMMA step followed by the inner product of its result with another tensor
+        if (i + 1 < nSteps && (steps[i + 1].a == nInputs + i || steps[i + 1].b == nInputs + i)) {
+            const bool tIsA = steps[i + 1].a == nInputs + i;
+            GettChoice gc2{0, false};
+            if (choose_kind(geoms[i + 1], gc2, ctx->microLog4) == KIND_REDUCE && fusable_pair(g, kind, gc, geoms[i + 1], tIsA)) {
+                closeMicro();
+                void *outp = nullptr;
+                { int st = pl->pool.alloc(0, &outp); if (st != QTB_OK) return bail(st); }
+                const int dId = tIsA ? steps[i + 1].b : steps[i + 1].a;
+                PlanSeg sg; sg.micro = false; sg.fused = true; sg.g = g; sg.kind = KIND_GETT; sg.gc = gc; sg.nSteps = 2;
+                sg.A = dev[s.a]; sg.B = dev[s.b]; sg.C = (double2 *)outp; sg.g2 = geoms[i + 1]; sg.tIsA = tIsA; sg.D = dev[dId];
+                pl->segs.push_back(sg);
+                dev[nInputs + i] = nullptr;                       // the intermediate is never materialised
+                dev[nInputs + i + 1] = (double2 *)outp;
+                pl->units += (long long)geoms[i + 1].units();
+                if (s.a >= nInputs) pl->pool.release(rank[s.a], dev[s.a]);
+                if (s.b >= nInputs) pl->pool.release(rank[s.b], dev[s.b]);
+                if (dId >= nInputs) pl->pool.release(rank[dId], dev[dId]);
+                ++i;                                              // the inner-product step is consumed
+                continue;
+            }
+        }
         void *cp = nullptr;
         { int st = pl->pool.alloc(g.rC, &cp); if (st != QTB_OK) return bail(st); }
         dev[nInputs + i] = (double2 *)cp;
-        pl->units += (long long)g.units();
         if (kind == KIND_MICRO) {
             PendingStep ps;
             make_devstep(g, dev[s.a], dev[s.b], dev[nInputs + i], KIND_MICRO, ps.st);
@@ -153,7 +180,7 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
     pl->nSteps = nSteps;
     pl->outDev = dev[nT - 1]; pl->outRank = rank[nT - 1];
     pl->launches = 0;
-    for (const PlanSeg &sg : pl->segs) pl->launches += (!sg.micro && sg.kind == KIND_REDUCE) ? 2 : 1;
+    for (const PlanSeg &sg : pl->segs) pl->launches += (!sg.micro && (sg.kind == KIND_REDUCE || sg.fused)) ? 2 : 1;
     // ---- assemble micro blobs into one device allocation
     if (!microBlobs.empty()) {
         std::vector<uint64_t> offs(microBlobs.size());

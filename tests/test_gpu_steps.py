@@ -253,3 +253,43 @@ def test_rank15_result_property(engine):
     finally:
         if A is not None:
             A.free()
+
+
+@pytest.mark.parametrize("t_is_a", [True, False])
+@pytest.mark.parametrize("shape", [(7, 7, [0, 3], [5, 1]), (6, 8, [1, 2], [7, 0]), (8, 6, [0, 4], [2, 5])])
+def test_fused_dmma_step_plus_inner_product(engine, t_is_a, shape):
+    """a big DMMA step whose rank-10 result is immediately contracted with another rank-10 tensor over all legs runs as
+    ONE fused kernel (the intermediate never reaches HBM): eager path (held-back step) and compiled plan, both operand
+    orders, against the oracle's two separate steps"""
+    rA, rB, pA, pB = shape
+    A, B = _rand(rA, 31), _rand(rB, 32)
+    rT = rA + rB - 2 * len(pA)
+    assert rT == 10
+    D = _rand(rT, 33)
+    perm = np.random.default_rng(5).permutation(rT).tolist()           # leg i of T pairs with leg perm[i] of D
+    O.lib().qto_set_threads(16)
+    T = O.contract(A, rA, B, rB, pA, pB)
+    if t_is_a:
+        ref = O.contract(T, rT, D, rT, list(range(rT)), perm)
+        posA2, posB2 = list(range(rT)), perm
+    else:
+        order = np.argsort(perm).tolist()                               # D is operand A: its legs in increasing order
+        posA2, posB2 = list(range(rT)), order                           # leg j of D pairs with leg order[j] of T
+        ref = O.contract(D, rT, T, rT, posA2, posB2)
+    # eager path
+    before = engine.stats()
+    ta, tb, td = engine.tensor(rA, A), engine.tensor(rB, B), engine.tensor(rT, D)
+    tt = engine.contract(ta, tb, pA, pB)
+    out = engine.contract(tt, td, posA2, posB2) if t_is_a else engine.contract(td, tt, posA2, posB2)
+    val = out.scalar()
+    after = engine.stats()
+    assert abs(val - ref[0]) <= 1e-11 * max(1.0, abs(ref[0])), (val, ref[0])
+    assert after["launches"] - before["launches"] <= 3                  # uploads + fused kernel + partial reduction
+    for t in (ta, tb, td, tt, out):
+        t.free()
+    # compiled plan: inputs 0,1,2 = A, B, D; step 0 -> id 3 (T); step 1 -> id 4
+    steps = [(0, 1, pA, pB), ((3, 2, posA2, posB2) if t_is_a else (2, 3, posA2, posB2))]
+    plan = engine.plan([rA, rB, rT], steps)
+    got = plan.run_host([A, B, D])[0]
+    assert plan.launches == 2 and abs(got - ref[0]) <= 1e-11 * max(1.0, abs(ref[0]))
+    plan.destroy()

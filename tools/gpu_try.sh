@@ -1,9 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "cli or minfill" 2>&1 | tail -6 | tee gpurun_out/try.log
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "fused or config2 or plan_api or random_leg or qaoa30" 2>&1 | tail -8 | tee gpurun_out/try.log
+QTB_GETT_C1=1 timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "fused or config2" 2>&1 | tail -3 | tee -a gpurun_out/try.log
 timeout 600 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_try.log
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_try.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'sliced', d['sliced']['ms_per_amplitude'], d['minfill_plan'])
+d=json.loads(open('gpurun_out/bench_try.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['config']['plan_launches_per_term'], d['kernel_time_ms_by_kind'], 'roof', d['roofline']['achieved'], 'sliced', d['sliced']['ms_per_amplitude'], d['sliced']['matches_reference_1e-10'], 'minfill', d['minfill_plan']['ms_per_term'], d['minfill_plan']['matches_reference_1e-10'])
 PY
