@@ -49,7 +49,7 @@ static const int MICRO_MAX_RANK = 7;
 struct GettChoice { int cfg; bool swap; };      // cfg: 0 C1/TK16 1 C1/TK4 2 C2/TK16 3 C2/TK4 4 C3/TK16 5 C3/TK4
 
 typedef void (*GettKernel)(const GettParams);
-struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; };
+struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; int drows; };   // drows: dotD rows per ring stage (fused variants)
 // C1: 128x64 tile, compute-bound big x big;  C2: 256x16;  C3: 256x8 (N <= 4 padded) -- streaming
 static GettInst g_gett[11] = {
     {k_gett<4, 2, 4, 4, 16, 3>, 128, 64, 16, GettCfg<4, 2, 4, 4, 16, 3>::NT, GettCfg<4, 2, 4, 4, 16, 3>::SMEM, 1},
@@ -65,8 +65,8 @@ static GettInst g_gett[11] = {
     // C1 "3M", 8 math warps of 32x16 (more registers per warp: double-buffered fragments)
     {k_gett<2, 4, 4, 2, 16, 5, 1>, 64, 64, 16, GettCfg<2, 4, 4, 2, 16, 5, 1>::NT, GettCfg<2, 4, 4, 2, 16, 5, 1>::SMEM, 1},
     // fused with the inner product that follows (FUSE = 1): variants of 6 (4M) and 7 (3M)
-    {k_gett<4, 4, 4, 2, 16, 3, 0, 1>, 128, 64, 16, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::NT, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::SMEM, 1},
-    {k_gett<4, 4, 2, 2, 16, 5, 1, 1>, 64, 64, 16, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::NT, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::SMEM, 1},
+    {k_gett<4, 4, 4, 2, 16, 3, 0, 1>, 128, 64, 16, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::NT, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::SMEM, 1, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::DROWS},
+    {k_gett<4, 4, 2, 2, 16, 5, 1, 1>, 64, 64, 16, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::NT, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::SMEM, 1, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::DROWS},
 };
 static int fused_variant_of(int cfg) { return cfg == 6 ? 9 : cfg == 7 ? 10 : -1; }
 static bool fusion_enabled() {
@@ -222,7 +222,7 @@ static bool fusable_pair(const StepGeom &g1, int kind1, const GettChoice &gc1, c
     return true;
 }
 // shDx / shDy of the fused kernel: where each x / y bit of the tile kernel lands inside D's element index
-static void add_fusion(const StepGeom &g2, bool tIsA, const double2 *D, double2 *partial, GettParams &p) {
+static void add_fusion(const StepGeom &g2, bool tIsA, const double2 *D, double2 *partial, const GettInst &inst, GettParams &p) {
     // leg l of T pairs with leg dLeg[l] of D
     int dLeg[QTB_MAXR];
     for (int j = 0; j < g2.k; j++) {
@@ -233,6 +233,14 @@ static void add_fusion(const StepGeom &g2, bool tIsA, const double2 *D, double2 
     for (int j = 0; j < p.ybits; j++) p.shDy[j] = (uint8_t)(2 * dLeg[p.shCy[j] / 2] + (p.shCy[j] & 1));
     p.dotD = D;
     p.dotPartial = partial;
+    // load order of one dotD piece (TM x drows): slot bits follow dotD's memory significance
+    const int TMB = ilog2i(inst.TM), RB = ilog2i(inst.drows);
+    struct CB { int shift, coord; };
+    std::vector<CB> v;
+    for (int j = 0; j < TMB; j++) v.push_back({p.shDx[j], j});
+    for (int j = 0; j < RB; j++) v.push_back({p.shDy[j], TMB + j});
+    std::sort(v.begin(), v.end(), [](const CB &a, const CB &b) { return a.shift < b.shift; });
+    for (size_t j = 0; j < v.size(); j++) p.permD[j] = (uint8_t)v[j].coord;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -569,9 +577,9 @@ static int enqueue_fused(qtb_ctx *ctx, const StepGeom &g1, const GettChoice &gc1
                          const StepGeom &g2, bool tIsA, const double2 *D, double2 *out, cudaStream_t s) {
     GettParams p;
     build_gett(g1, gc1, A1, B1, nullptr, p);
-    add_fusion(g2, tIsA, D, ctx->reduceScratch, p);
     const int cfg = fused_variant_of(gc1.cfg);
     const GettInst &inst = g_gett[cfg];
+    add_fusion(g2, tIsA, D, ctx->reduceScratch, inst, p);
     const unsigned nTiles = p.nTilesX * p.nTilesY;
     const unsigned grid = std::min<unsigned>(nTiles, (unsigned)(ctx->numSMs * inst.occ));
     inst.fn<<<grid, inst.NT, inst.smem, s>>>(p);

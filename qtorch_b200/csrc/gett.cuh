@@ -50,6 +50,7 @@ struct GettParams {
     const double2 *dotD;
     double2 *dotPartial;              // one partial sum per CTA
     uint8_t shDx[32], shDy[32];
+    uint8_t permD[16];                // load order of a dotD tile piece: slot bit j -> coordinate bit (x bits, then the piece's y bits)
 };
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, const double a, const double b) {
@@ -107,7 +108,13 @@ struct GettCfg {
     static constexpr int YS = (TK * LDY > TN * LDK) ? TK * LDY : TN * LDK;
     static constexpr int STAGE_ELEMS = XS + YS;
     static constexpr int XROUNDS = (TM * TK + NPT - 1) / NPT, YROUNDS = (TN * TK + NPT - 1) / NPT;
-    static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 2 * XROUNDS + 2 * YROUNDS + (FUSE ? TM + TN + 64 : 0);   // uint32 tables
+    // fused inner product: the matching dotD tile (TM x TN) rides through the same ring after a tile's last k-chunk,
+    // cut into DP pieces of TN/DP rows ([y][x] layout, row stride TM+2) so that each piece fits one stage
+    static constexpr int dpFor(int dp) { return (TN / dp) * (TM + 2) <= STAGE_ELEMS ? dp : dpFor(dp * 2); }
+    static constexpr int DP = FUSE ? dpFor(1) : 0;
+    static constexpr int DROWS = FUSE ? TN / (DP ? DP : 1) : 0;                 // y rows per piece
+    static constexpr int DROUNDS = FUSE ? (DROWS * TM + NPT - 1) / NPT : 0;
+    static constexpr int TAB = 2 * TM + 2 * TN + 2 * TK + 2 * XROUNDS + 2 * YROUNDS + (FUSE ? TM + TN + 64 + 2 * DROUNDS : 0);   // uint32 tables
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 16 + TAB * 4 + 2 * STAGES * 8 + 16 + 32 * FUSE + (6 + 2 * FUSE) * sizeof(HiTab);
 };
 
@@ -157,7 +164,8 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
     uint32_t *tXx = tab, *tCx = tXx + TM, *tYy = tCx + TM, *tCy = tYy + TN, *tXk = tCy + TN, *tYk = tXk + TK;
     uint32_t *dXo = tYk + TK, *dXs = dXo + XROUNDS, *dYo = dXs + XROUNDS, *dYs = dYo + YROUNDS;   // per-round deltas
     uint32_t *tDx = dYs + YROUNDS, *tDy = tDx + (FUSE ? TM : 0);                                   // fused dot: tile-local -> dotD offset
-    double2 *dotRed = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(tDy + (FUSE ? TN : 0)) + 15) & ~(uintptr_t)15);   // NW partials
+    uint32_t *dDo = tDy + (FUSE ? TN : 0), *dDs = dDo + Cfg::DROUNDS;                                // dotD piece: per-round deltas
+    double2 *dotRed = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(dDs + Cfg::DROUNDS) + 15) & ~(uintptr_t)15);   // NW partials
     uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(FUSE ? (uint32_t *)(dotRed + NW) : dYs + YROUNDS) + 7) & ~(uintptr_t)7);
     HiTab *hi = reinterpret_cast<HiTab *>(bars + 2 * STAGES);     // [0] X by tile-x, [1] Y by tile-y, [2] X by chunk, [3] Y by chunk, [4] C by tile-x, [5] C by tile-y
     const uint32_t barBase = (uint32_t)__cvta_generic_to_shared(bars);        // full[s] = barBase + 8 s, empty[s] = full + 8 STAGES
@@ -223,12 +231,22 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         dYo[r] = tYy[yl] + tYk[kly];
         dYs[r] = (kly * ysK + yl * ysY) * 16;
     }
+    constexpr int DEB = FUSE ? TMB + ilog2(Cfg::DROWS ? Cfg::DROWS : 1) : 0;        // slot bits of one dotD piece
+    if (FUSE) {
+        for (int r = tid; r < Cfg::DROUNDS; r += NT) {
+            const uint32_t w = coordOf((uint32_t)r << 7, p.permD, DEB);
+            const uint32_t xl = w & (TM - 1), yl = w >> TMB;
+            dDo[r] = tDx[xl] + tDy[yl];
+            dDs[r] = (yl * (TM + 2) + xl) * 16;
+        }
+    }
     __syncthreads();
 
     const uint32_t smemBase = (uint32_t)__cvta_generic_to_shared(stages);
     const uint32_t nTiles = p.nTilesX * p.nTilesY, nChunks = p.nChunks;
     const uint32_t myTiles = blockIdx.x < nTiles ? (nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t total = myTiles * nChunks;
+    const uint32_t perTile = nChunks + (FUSE ? Cfg::DP : 0);          // ring slots per tile: k-chunks, then dotD pieces
+    const uint32_t total = myTiles * perTile;
 
     if (warp >= NW) {
         // ================= producer warpgroup =================
@@ -248,12 +266,30 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         const int yRounds = (int)((nYElems + Cfg::NPT - 1) / Cfg::NPT);
         const bool yLane = ptid < nYElems;
         const bool xLane = ptid < (uint32_t)(TM * TK);
+        uint32_t dOff0 = 0, dSm0 = 0;
+        if (FUSE) {
+            const uint32_t w = coordOf(ptid & ((1u << DEB) - 1), p.permD, DEB);
+            const uint32_t xl = w & (TM - 1), yl = w >> TMB;
+            dOff0 = tDx[xl] + tDy[yl];
+            dSm0 = (yl * (TM + 2) + xl) * 16;
+        }
         uint32_t ti = 0, ch = 0;
         for (uint32_t q = 0; q < total; q++) {
             const uint32_t stage = q % STAGES, round = q / STAGES;
             if (round > 0) mbar_wait(barBase + 8 * (STAGES + stage), (round - 1) & 1);
             const uint32_t tile = blockIdx.x + ti * gridDim.x;
             const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
+            if (FUSE && ch >= nChunks) {
+                // dotD piece (ch - nChunks): rows [piece*DROWS, (piece+1)*DROWS) of this tile, gathered in dotD's memory order
+                const uint32_t piece = ch - nChunks;
+                const double2 *gd = p.dotD + hitab_lookup(hi[6], tx, xParts) + hitab_lookup(hi[7], ty, yParts) + tDy[piece * Cfg::DROWS] + dOff0;
+                const uint32_t sbd = smemBase + stage * (Cfg::STAGE_ELEMS * 16);
+#pragma unroll 8
+                for (int r = 0; r < Cfg::DROUNDS; r++) cp_async16(sbd + dSm0 + dDs[r], gd + dDo[r]);
+                cp_async_mbar_arrive(barBase + 8 * stage);
+                if (++ch == perTile) { ch = 0; ++ti; }
+                continue;
+            }
             const double2 *gx = p.X + hitab_lookup(hi[0], tx, xParts) + hitab_lookup(hi[2], ch, kParts) + xOff0;
             const double2 *gy = p.Y + hitab_lookup(hi[1], ty, yParts) + hitab_lookup(hi[3], ch, kParts) + yOff0;
             const uint32_t sb = smemBase + stage * (Cfg::STAGE_ELEMS * 16);
@@ -266,7 +302,7 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
                 for (int r = 0; r < yRounds; r++) cp_async16(sb + ySm0 + dYs[r], gy + dYo[r]);
             }
             cp_async_mbar_arrive(barBase + 8 * stage);
-            if (++ch == nChunks) { ch = 0; ++ti; }
+            if (++ch == perTile) { ch = 0; ++ti; }
         }
         cp_async_wait<0>();
         return;
@@ -294,6 +330,7 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         }
         const uint32_t stage = q % STAGES;
         mbar_wait(barBase + 8 * stage, (q / STAGES) & 1);
+        if (!FUSE || ch < nChunks) {
         const double2 *xs_ = stages + (size_t)stage * Cfg::STAGE_ELEMS;
         const double2 *ys_ = xs_ + Cfg::XS;
         if (MODE3M) {
@@ -364,42 +401,35 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
                     for (int j = 0; j < FY; j++) dmma884(accI[i][j][0], accI[i][j][1], xf[i].y, yf[j].x);
             }
         }
-        // stage consumed: hand it back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(barBase + 8 * (STAGES + stage));
-
-        if (ch == nChunks - 1) {
-            const uint32_t tile = blockIdx.x + ti * gridDim.x;
-            const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
-            double2 *cb = p.C + hitab_lookup(hi[4], tx, xParts) + hitab_lookup(hi[5], ty, yParts);
-            const double2 *db = FUSE ? p.dotD + hitab_lookup(hi[6], tx, xParts) + hitab_lookup(hi[7], ty, yParts) : nullptr;
-            if (FUSE) {
-                // gather this lane's dotD elements first (all loads in flight together), then combine
-                double2 dv[FX][FY][2];
-#pragma unroll
-                for (int i = 0; i < FX; i++) {
-                    const uint32_t ox = tDx[wx0 + i * 8 + g];
-#pragma unroll
-                    for (int j = 0; j < FY; j++) {
-                        const int y0 = wy0 + j * 8 + 2 * t;
-                        dv[i][j][0] = (uint32_t)y0 < nyValid ? db[ox + tDy[y0]] : make_double2(0.0, 0.0);
-                        dv[i][j][1] = (uint32_t)(y0 + 1) < nyValid ? db[ox + tDy[y0 + 1]] : make_double2(0.0, 0.0);
-                    }
-                }
+        } else {
+            // dotD piece in this stage ([y][x], row stride TM+2): the warps whose rows it holds fold it into the inner product
+            const uint32_t piece = ch - nChunks;
+            if ((uint32_t)wy0 / (uint32_t)(Cfg::DROWS ? Cfg::DROWS : 1) == piece) {
+                const double2 *dt = stages + (size_t)stage * Cfg::STAGE_ELEMS;
+                const uint32_t yBase = (uint32_t)wy0 - piece * Cfg::DROWS;
 #pragma unroll
                 for (int i = 0; i < FX; i++)
 #pragma unroll
                     for (int j = 0; j < FY; j++)
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
+                            const double2 dv = dt[(yBase + j * 8 + 2 * t + h) * (TM + 2) + wx0 + i * 8 + g];
                             double re, im;
                             if (MODE3M) { re = accR[i][j][h] - accI[i][j][h]; im = acc3[i][j][h] - accR[i][j][h] - accI[i][j][h]; }
                             else { re = accR[i][j][h]; im = accI[i][j][h]; }
-                            dotR = fma(re, dv[i][j][h].x, dotR); dotR = fma(-im, dv[i][j][h].y, dotR);
-                            dotI = fma(re, dv[i][j][h].y, dotI); dotI = fma(im, dv[i][j][h].x, dotI);
+                            dotR = fma(re, dv.x, dotR); dotR = fma(-im, dv.y, dotR);
+                            dotI = fma(re, dv.y, dotI); dotI = fma(im, dv.x, dotI);
                         }
             }
-            if (!FUSE) {
+        }
+        // stage consumed: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(barBase + 8 * (STAGES + stage));
+
+        if (!FUSE && ch == nChunks - 1) {
+            const uint32_t tile = blockIdx.x + ti * gridDim.x;
+            const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
+            double2 *cb = p.C + hitab_lookup(hi[4], tx, xParts) + hitab_lookup(hi[5], ty, yParts);
 #pragma unroll
             for (int i = 0; i < FX; i++) {
                 const uint32_t ox = tCx[wx0 + i * 8 + g];
@@ -417,11 +447,8 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
                     if ((uint32_t)(y0 + 1) < nyValid) cb[ox + tCy[y0 + 1]] = make_double2(re1, im1);
                 }
             }
-            }
-            ch = 0; ++ti;
-        } else {
-            ++ch;
         }
+        if (++ch == perTile) { ch = 0; ++ti; }
     }
     if (FUSE) {
         // CTA partial of the fused inner product: shuffle tree per warp, then a named barrier over the math warps only
