@@ -77,6 +77,13 @@ int qtb_tensor_upload(qtb_ctx *ctx, qtb_tensor t, const double *host_re_im);
 int qtb_tensor_download(qtb_ctx *ctx, qtb_tensor t, double *host_re_im);
 /* LGContract reading GetTensorVals()[0] (LineGraph.h:388) / mFinalVal = C[0] (Network.h:964).        */
 int qtb_read_scalar(qtb_ctx *ctx, qtb_tensor t, double out_re_im[2]);
+/* The same read in two halves, for callers that keep several networks in flight: `begin` launches everything still
+ * deferred and enqueues the 16-byte device->host copy right behind the work that produces t (no synchronisation);
+ * `end` waits for THAT copy only -- not for steps of other networks enqueued after it -- and releases the handle.
+ * The tensor may be freed (qtb_tensor_free) between the two calls.                                                */
+typedef struct qtb_scalar_read_s qtb_scalar_read;
+int qtb_read_scalar_begin(qtb_ctx *ctx, qtb_tensor t, qtb_scalar_read **out);
+int qtb_read_scalar_end(qtb_ctx *ctx, qtb_scalar_read *read, double out_re_im[2]);
 
 /* ---- the hot path: replaces Network::ContractIndices (Network.h:876-971) ------------------------- */
 /* C = contract(A, B) over k shared legs.  Asynchronous on the ctx stream; tiny steps may be deferred
@@ -113,6 +120,17 @@ int qtb_plan_output_rank(qtb_plan *plan);
  * Only for plans whose inputs all have rank <= 5 (gate / state / measurement tensors).                  */
 int qtb_plan_stage_inputs(qtb_ctx *ctx, qtb_plan *plan, int slot, const double *const *host_inputs);
 int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *plan, int slot);
+/* Index-sliced networks (SURVEY 8e "Slices"): the 4^s slices of one network share every step that does not touch a cut
+ * wire.  The caller orders the plan so that its first n_invariant_steps steps depend only on inputs that are identical
+ * in all slots (qtorch_b200/slicing.py:hoist_invariant does that); their results are kept alive for the whole call.
+ * qtb_plan_run_slots then runs that prefix ONCE, the remaining steps once per listed slot, and returns the sum of the
+ * scalar outputs (host_each, if not NULL, receives the n individual (re, im) pairs) with a single synchronisation.
+ * n_invariant_steps = 0 gives an ordinary plan; qtb_plan_run_slots on it just runs the whole plan per slot.        */
+int qtb_plan_create_sliced(qtb_ctx *ctx, int n_inputs, const int *input_ranks, int n_steps, const qtb_plan_step *steps,
+                           int n_invariant_steps, qtb_plan **out);
+int qtb_plan_run_slots(qtb_ctx *ctx, qtb_plan *plan, const int *slots, int n, double *host_sum, double *host_each);
+/* sum of 4^(rC+k) over the invariant prefix (done once per qtb_plan_run_slots call, not once per slot) */
+long long qtb_plan_prefix_units(qtb_plan *plan);
 /* Grouped evaluation of n independent plans with scalar outputs (e.g. the 45 per-edge <ZiZj> networks of one QAOA
  * objective evaluation, maxcut.cpp:171-198): all inputs are uploaded, plans that consist of micro-steps only run in
  * ONE launch (one CTA per plan), the n scalars come back with one synchronisation.

@@ -23,9 +23,9 @@ ABI_SYMBOLS = [
     "qtb_abi_version", "qtb_status_string", "qtb_last_error", "qtb_device_count",
     "qtb_ctx_create", "qtb_ctx_destroy", "qtb_ctx_sync", "qtb_ctx_flush", "qtb_ctx_stream",
     "qtb_tensor_alloc", "qtb_tensor_free", "qtb_tensor_rank", "qtb_tensor_device_ptr",
-    "qtb_tensor_upload", "qtb_tensor_download", "qtb_read_scalar", "qtb_contract",
+    "qtb_tensor_upload", "qtb_tensor_download", "qtb_read_scalar", "qtb_read_scalar_begin", "qtb_read_scalar_end", "qtb_contract",
     "qtb_plan_create", "qtb_plan_destroy", "qtb_plan_run_host", "qtb_plan_upload_inputs",
-    "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_stage_inputs", "qtb_plan_run_device_slot", "qtb_plans_run_batched", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
+    "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_stage_inputs", "qtb_plan_run_device_slot", "qtb_plan_create_sliced", "qtb_plan_run_slots", "qtb_plan_prefix_units", "qtb_plans_run_batched", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
     "qtb_comm_unique_id", "qtb_comm_init", "qtb_comm_destroy", "qtb_allreduce_sum",
     "qtb_ctx_stats", "qtb_ctx_reset_stats", "qtb_ctx_timer_start", "qtb_ctx_timer_stop", "qtb_ctx_set_micro_limit", "qtb_ctx_get_micro_limit", "qtb_ctx_trace_enable", "qtb_ctx_trace_read",
 ]
@@ -86,6 +86,8 @@ def load_library():
     L.qtb_tensor_upload.argtypes = [vp, vp, vp]
     L.qtb_tensor_download.argtypes = [vp, vp, vp]
     L.qtb_read_scalar.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_double)]
+    L.qtb_read_scalar_begin.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    L.qtb_read_scalar_end.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_double)]
     L.qtb_contract.argtypes = [vp, vp, vp, ci, cpi, cpi, vp]
     L.qtb_plan_create.argtypes = [vp, ci, cpi, ci, ctypes.POINTER(PlanStep), ctypes.POINTER(vp)]
     L.qtb_plan_destroy.argtypes = [vp, vp]
@@ -95,6 +97,10 @@ def load_library():
     L.qtb_plan_read_output.argtypes = [vp, vp, vp]
     L.qtb_plan_stage_inputs.argtypes = [vp, vp, ci, ctypes.POINTER(vp)]
     L.qtb_plan_run_device_slot.argtypes = [vp, vp, ci]
+    L.qtb_plan_create_sliced.argtypes = [vp, ci, cpi, ci, ctypes.POINTER(PlanStep), ci, ctypes.POINTER(vp)]
+    L.qtb_plan_run_slots.argtypes = [vp, vp, cpi, ci, vp, vp]
+    L.qtb_plan_prefix_units.restype = ctypes.c_longlong
+    L.qtb_plan_prefix_units.argtypes = [vp]
     L.qtb_ctx_set_micro_limit.argtypes = [vp, ci]
     L.qtb_ctx_get_micro_limit.argtypes = [vp]
     L.qtb_ctx_timer_start.argtypes = [vp]
@@ -164,7 +170,7 @@ class Plan:
     """Compiled contraction plan.  ``steps`` = [(a, b, posA, posB), ...] with tensor ids in the reference's
     mCreatedFrom numbering (inputs 0..n-1, result of step i = n+i)."""
 
-    def __init__(self, engine, input_ranks, steps):
+    def __init__(self, engine, input_ranks, steps, invariant_steps=0):
         self.engine = engine
         self.input_ranks = list(input_ranks)
         arr = (PlanStep * len(steps))()
@@ -173,7 +179,8 @@ class Plan:
             for j, (x, y) in enumerate(zip(pa, pb)):
                 arr[i].pos_a[j], arr[i].pos_b[j] = x, y
         h = ctypes.c_void_p()
-        _check(engine.lib.qtb_plan_create(engine.ctx, len(input_ranks), _iarr(self.input_ranks), len(steps), arr, ctypes.byref(h)))
+        _check(engine.lib.qtb_plan_create_sliced(engine.ctx, len(input_ranks), _iarr(self.input_ranks), len(steps), arr,
+                                                 int(invariant_steps), ctypes.byref(h)))
         self.handle = h
         self.n_steps = len(steps)
 
@@ -210,6 +217,18 @@ class Plan:
 
     def run_device_slot(self, slot):
         _check(self.engine.lib.qtb_plan_run_device_slot(self.engine.ctx, self.handle, slot))
+
+    def run_slots(self, slots, each=False):
+        """Sum of the scalar outputs over the staged input slots: invariant prefix once, the rest per slot, one sync."""
+        slots = list(slots)
+        total = np.zeros(1, dtype=np.complex128)
+        per = np.zeros(max(len(slots), 1), dtype=np.complex128)
+        _check(self.engine.lib.qtb_plan_run_slots(self.engine.ctx, self.handle, _iarr(slots), len(slots), total.ctypes.data, per.ctypes.data))
+        return (complex(total[0]), per[:len(slots)]) if each else complex(total[0])
+
+    @property
+    def prefix_units(self):
+        return self.engine.lib.qtb_plan_prefix_units(self.handle)
 
     def read_output(self):
         out = np.empty(4 ** self.output_rank, dtype=np.complex128)
@@ -250,8 +269,8 @@ class Engine:
         _check(self.lib.qtb_contract(self.ctx, a.handle, b.handle, k, _iarr(pos_a), _iarr(pos_b), c.handle))
         return c
 
-    def plan(self, input_ranks, steps):
-        return Plan(self, input_ranks, steps)
+    def plan(self, input_ranks, steps, invariant_steps=0):
+        return Plan(self, input_ranks, steps, invariant_steps)
 
     def sync(self):
         _check(self.lib.qtb_ctx_sync(self.ctx))

@@ -48,6 +48,43 @@ int qth_contract_linegraph(const char *qasm, const char *measure, const char *qb
     }
 }
 
+// The same call split in two, so that a caller with many networks (the 60 <ZiZj> terms of one QAOA evaluation) can
+// overlap the host bookkeeping of network i+1 with the device work of network i: `begin` parses, reduces, walks the
+// ordering and enqueues every step (no synchronisation -- Network::GetFinalValue is lazy); `end` reads the scalar back.
+struct QthJob { std::shared_ptr<Network> net; bool ok; };
+
+void *qth_linegraph_begin(const char *qasm, const char *measure, const char *qbbOut, int reduce) {
+    try {
+        auto net = std::make_shared<Network>(qasm, measure);
+        if (reduce) net->ReduceCircuit();
+        LineGraph lg(net);
+        lg.SetQBBOutFiles("/dev/null", qbbOut, "/dev/null");
+        const bool ok = lg.LGContract();
+        net->PrefetchFinalValue();        // launches what is still held back and queues the scalar read right behind it
+        return new QthJob{net, ok};
+    } catch (std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+int qth_linegraph_end(void *job, double value[2], long long *flops, int *nodes) {
+    if (!job) { g_err = "null job"; return 1; }
+    QthJob *j = static_cast<QthJob *>(job);
+    int rc = j->ok ? 0 : 2;
+    try {
+        const std::complex<double> v = j->net->GetFinalValue();
+        value[0] = v.real(); value[1] = v.imag();
+        if (flops) *flops = j->net->getNumFloatOps();
+        if (nodes) *nodes = static_cast<int>(j->net->GetAllNodes().size());
+    } catch (std::exception &e) {
+        g_err = e.what();
+        rc = 1;
+    }
+    delete j;
+    return rc;
+}
+
 // ContractionTools(qasm, measure).ContractGivenSequence(pairs): replay of a recorded plan (mCreatedFrom pairs).
 int qth_contract_sequence(const char *qasm, const char *measure, const int *pairs, int nPairs, double value[2],
                           long long *flops, int *nodes, double *secondsAfterParse) {

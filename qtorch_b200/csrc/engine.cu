@@ -345,6 +345,8 @@ struct PendingUpload { double2 *dst; size_t payloadOff; uint32_t elems; };
 
 struct TraceRec { cudaEvent_t e0, e1; int rA, rB, k, kernel; };
 
+struct qtb_scalar_read_s { double *pinned = nullptr; cudaEvent_t done = nullptr; };
+
 struct qtb_ctx_s {
     int device = 0;
     int numSMs = 148;
@@ -356,6 +358,7 @@ struct qtb_ctx_s {
     size_t ringSize = (size_t)32 << 20, ringCur = 0;
     cudaEvent_t ringEvent = nullptr; bool ringEventValid = false;
     double *scalarPinned = nullptr;
+    std::vector<qtb_scalar_read_s *> freeReads;   // recycled handles of qtb_read_scalar_begin/end
     uint64_t *zeroOffsetDev = nullptr;          // blobOffsets[0] = 0 for single-blob launches
     double2 *reduceScratch = nullptr;           // split-K partials: [REDUCE_MAX_BLOCKS][16]
     // deferred micro work
@@ -674,6 +677,7 @@ int qtb_ctx_destroy(qtb_ctx *ctx) {
     if (ctx->commBuf) cudaFree(ctx->commBuf);
     for (auto &t : ctx->traceRecs) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     ctx->pool.destroy();
+    for (qtb_scalar_read_s *r : ctx->freeReads) { cudaFreeHost(r->pinned); cudaEventDestroy(r->done); delete r; }
     cudaFreeHost(ctx->ringHost); cudaFree(ctx->ringDev); cudaFreeHost(ctx->scalarPinned); cudaFree(ctx->zeroOffsetDev); cudaFree(ctx->reduceScratch);
     cudaEventDestroy(ctx->ringEvent);
     cudaStreamDestroy(ctx->stream);
@@ -766,6 +770,41 @@ int qtb_read_scalar(qtb_ctx *ctx, qtb_tensor t, double out[2]) {
     CU(cudaStreamSynchronize(ctx->stream));
     out[0] = ctx->scalarPinned[0]; out[1] = ctx->scalarPinned[1];
     ctx->stats.bytes_d2h += 16;
+    return QTB_OK;
+}
+
+int qtb_read_scalar_begin(qtb_ctx *ctx, qtb_tensor t, qtb_scalar_read **out) {
+    if (!ctx || !t || !out) return fail(QTB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!t->hasData || !t->d) return fail(QTB_ERR_EMPTY_INPUT, "tensor has no data");
+    ST(flush_locked(ctx));
+    qtb_scalar_read *r = nullptr;
+    if (!ctx->freeReads.empty()) { r = ctx->freeReads.back(); ctx->freeReads.pop_back(); }
+    else {
+        r = new qtb_scalar_read_s();
+        if (cudaMallocHost((void **)&r->pinned, 16) != cudaSuccess || cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming) != cudaSuccess) {
+            if (r->pinned) cudaFreeHost(r->pinned);
+            delete r;
+            cudaGetLastError();
+            return fail(QTB_ERR_OOM, "scalar read slot allocation failed");
+        }
+    }
+    cudaError_t e = cudaMemcpyAsync(r->pinned, t->d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(r->done, ctx->stream);
+    if (e != cudaSuccess) { ctx->freeReads.push_back(r); return fail(QTB_ERR_CUDA, cudaGetErrorString(e)); }
+    ctx->stats.bytes_d2h += 16;
+    *out = r;
+    return QTB_OK;
+}
+
+int qtb_read_scalar_end(qtb_ctx *ctx, qtb_scalar_read *r, double out[2]) {
+    if (!ctx || !r) return fail(QTB_ERR_INVALID, "null argument");
+    cudaError_t e = cudaEventSynchronize(r->done);           // outside the lock: other threads may keep enqueueing
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (out) { out[0] = r->pinned[0]; out[1] = r->pinned[1]; }
+    ctx->freeReads.push_back(r);
+    if (e != cudaSuccess) return fail(QTB_ERR_CUDA, cudaGetErrorString(e));
     return QTB_OK;
 }
 

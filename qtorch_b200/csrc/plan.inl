@@ -31,6 +31,10 @@ struct qtb_plan_s {
     long long units = 0; int nSteps = 0, nMicroSteps = 0; int launches = 0;
     cudaGraphExec_t graph = nullptr; bool graphTried = false;
     std::vector<uint8_t *> slotDev;          // extra resident copies of the small-input blob
+    // slot-invariant prefix (qtb_plan_create_sliced): segs[0..prefixSegs) do not depend on the inputs that differ between
+    // slots, so qtb_plan_run_slots runs them once and only segs[prefixSegs..) per slot; their results stay live.
+    int nPrefixSteps = 0; size_t prefixSegs = 0; int launchesPrefix = 0; long long prefixUnits = 0;
+    cudaGraphExec_t graphPrefix = nullptr, graphSuffix = nullptr; bool partGraphsTried = false;
 };
 
 static bool plan_graphs_enabled() {
@@ -39,8 +43,10 @@ static bool plan_graphs_enabled() {
     return v == 1;
 }
 
-static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s) {
-    for (const PlanSeg &sg : pl->segs) {
+static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s, size_t segBegin = 0, size_t segEnd = (size_t)-1) {
+    if (segEnd > pl->segs.size()) segEnd = pl->segs.size();
+    for (size_t si = segBegin; si < segEnd; si++) {
+        const PlanSeg &sg = pl->segs[si];
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, s)); }
         if (sg.micro) {
@@ -64,7 +70,13 @@ static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s) {
 extern "C" {
 
 int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps, const qtb_plan_step *steps, qtb_plan **out) {
+    return qtb_plan_create_sliced(ctx, nInputs, inputRanks, nSteps, steps, 0, out);
+}
+
+int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps, const qtb_plan_step *steps, int nPrefix, qtb_plan **out) {
     if (!ctx || !out || nInputs < 0 || nSteps < 1 || (nInputs > 0 && !inputRanks) || !steps) return fail(QTB_ERR_INVALID, "bad plan arguments");
+    if (nPrefix < 0 || nPrefix > nSteps) return fail(QTB_ERR_INVALID, "bad invariant-prefix length");
+    if (nPrefix == nSteps) nPrefix = 0;              // nothing varies: an ordinary plan
     *out = nullptr;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ST(ensure_device(ctx));
@@ -127,14 +139,18 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
         for (auto &f : deferred) pl->pool.release(f.first, f.second);
         deferred.clear();
     };
+    pl->nPrefixSteps = nPrefix;
+    // a tensor made by the invariant prefix (or a plan input) must survive every slot's pass over the suffix
+    auto releasable = [&](int t, int atStep) { return t >= nInputs && !(atStep >= nPrefix && t < nInputs + nPrefix); };
     for (int i = 0; i < nSteps; i++) {
         const qtb_plan_step &s = steps[i];
         const StepGeom &g = geoms[i];
         GettChoice gc{0, false};
         const int kind = choose_kind(g, gc, ctx->microLog4);
         pl->units += (long long)g.units();
+        if (nPrefix > 0 && i == nPrefix) { closeMicro(); pl->prefixSegs = pl->segs.size(); pl->prefixUnits = pl->units - (long long)g.units(); }
         // fusion: this DMMA step followed by the inner product of its result with another tensor
-        if (i + 1 < nSteps && (steps[i + 1].a == nInputs + i || steps[i + 1].b == nInputs + i)) {
+        if (i + 1 < nSteps && i + 1 != nPrefix && (steps[i + 1].a == nInputs + i || steps[i + 1].b == nInputs + i)) {
             const bool tIsA = steps[i + 1].a == nInputs + i;
             GettChoice gc2{0, false};
             if (choose_kind(geoms[i + 1], gc2, ctx->microLog4) == KIND_REDUCE && fusable_pair(g, kind, gc, geoms[i + 1], tIsA)) {
@@ -148,9 +164,9 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
                 dev[nInputs + i] = nullptr;                       // the intermediate is never materialised
                 dev[nInputs + i + 1] = (double2 *)outp;
                 pl->units += (long long)geoms[i + 1].units();
-                if (s.a >= nInputs) pl->pool.release(rank[s.a], dev[s.a]);
-                if (s.b >= nInputs) pl->pool.release(rank[s.b], dev[s.b]);
-                if (dId >= nInputs) pl->pool.release(rank[dId], dev[dId]);
+                if (releasable(s.a, i)) pl->pool.release(rank[s.a], dev[s.a]);
+                if (releasable(s.b, i)) pl->pool.release(rank[s.b], dev[s.b]);
+                if (releasable(dId, i)) pl->pool.release(rank[dId], dev[dId]);
                 ++i;                                              // the inner-product step is consumed
                 continue;
             }
@@ -165,22 +181,27 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
             cur.push_back(ps);
             levelOf[nInputs + i] = ps.level + 1;
             pl->nMicroSteps++;
-            if (s.a >= nInputs) deferred.push_back({rank[s.a], (void *)dev[s.a]});
-            if (s.b >= nInputs) deferred.push_back({rank[s.b], (void *)dev[s.b]});
+            if (releasable(s.a, i)) deferred.push_back({rank[s.a], (void *)dev[s.a]});
+            if (releasable(s.b, i)) deferred.push_back({rank[s.b], (void *)dev[s.b]});
         } else {
             closeMicro();
             PlanSeg sg; sg.micro = false; sg.g = g; sg.kind = kind; sg.gc = gc; sg.nSteps = 1;
             sg.A = dev[s.a]; sg.B = dev[s.b]; sg.C = dev[nInputs + i];
             pl->segs.push_back(sg);
-            if (s.a >= nInputs) pl->pool.release(rank[s.a], dev[s.a]);
-            if (s.b >= nInputs) pl->pool.release(rank[s.b], dev[s.b]);
+            if (releasable(s.a, i)) pl->pool.release(rank[s.a], dev[s.a]);
+            if (releasable(s.b, i)) pl->pool.release(rank[s.b], dev[s.b]);
         }
     }
     closeMicro();
     pl->nSteps = nSteps;
     pl->outDev = dev[nT - 1]; pl->outRank = rank[nT - 1];
     pl->launches = 0;
-    for (const PlanSeg &sg : pl->segs) pl->launches += (!sg.micro && (sg.kind == KIND_REDUCE || sg.fused)) ? 2 : 1;
+    for (size_t si = 0; si < pl->segs.size(); si++) {
+        const PlanSeg &sg = pl->segs[si];
+        const int l = (!sg.micro && (sg.kind == KIND_REDUCE || sg.fused)) ? 2 : 1;
+        pl->launches += l;
+        if (si < pl->prefixSegs) pl->launchesPrefix += l;
+    }
     // ---- assemble micro blobs into one device allocation
     if (!microBlobs.empty()) {
         std::vector<uint64_t> offs(microBlobs.size());
@@ -214,6 +235,8 @@ int qtb_plan_destroy(qtb_ctx *ctx, qtb_plan *pl) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (pl->graph) cudaGraphExecDestroy(pl->graph);
+    if (pl->graphPrefix) cudaGraphExecDestroy(pl->graphPrefix);
+    if (pl->graphSuffix) cudaGraphExecDestroy(pl->graphSuffix);
     pl->pool.destroy();
     if (pl->inBlobHost) cudaFreeHost(pl->inBlobHost);
     if (pl->inBlobDev) cudaFree(pl->inBlobDev);
@@ -244,23 +267,30 @@ static int plan_upload_locked(qtb_ctx *ctx, qtb_plan *pl, const double *const *h
     return QTB_OK;
 }
 
+// capture segs[segBegin, segEnd) into an executable graph; nullptr (and no error) when capture is not possible
+static cudaGraphExec_t plan_capture(qtb_ctx *ctx, qtb_plan *pl, size_t segBegin, size_t segEnd) {
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const long long launchesBefore = ctx->stats.launches;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        int st = plan_enqueue(ctx, pl, ctx->stream, segBegin, segEnd);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        ctx->stats.launches = launchesBefore;
+        if (st == QTB_OK && e == cudaSuccess && g) {
+            if (cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { exec = nullptr; cudaGetLastError(); }
+        } else cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+    } else cudaGetLastError();
+    return exec;
+}
+
 static int plan_run_locked(qtb_ctx *ctx, qtb_plan *pl) {
     ST(ensure_device(ctx));
     ST(flush_locked(ctx));
     const bool useGraph = plan_graphs_enabled() && !ctx->trace && pl->segs.size() >= 3;
     if (useGraph && !pl->graphTried) {
         pl->graphTried = true;
-        cudaGraph_t g = nullptr;
-        const long long launchesBefore = ctx->stats.launches;
-        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            int st = plan_enqueue(ctx, pl, ctx->stream);
-            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-            ctx->stats.launches = launchesBefore;
-            if (st == QTB_OK && e == cudaSuccess && g) {
-                if (cudaGraphInstantiate(&pl->graph, g, 0) != cudaSuccess) { pl->graph = nullptr; cudaGetLastError(); }
-            } else cudaGetLastError();
-            if (g) cudaGraphDestroy(g);
-        } else cudaGetLastError();
+        pl->graph = plan_capture(ctx, pl, 0, pl->segs.size());
     }
     if (useGraph && pl->graph) {
         CU(cudaGraphLaunch(pl->graph, ctx->stream));
@@ -336,6 +366,59 @@ int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *pl, int slot) {
     CU(cudaMemcpyAsync(pl->inBlobDev, pl->slotDev[slot], pl->inBlobBytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return plan_run_locked(ctx, pl);
 }
+int qtb_plan_run_slots(qtb_ctx *ctx, qtb_plan *pl, const int *slots, int n, double *hostSum, double *hostEach) {
+    if (!ctx || !pl || !slots || n < 1 || !hostSum) return fail(QTB_ERR_INVALID, "bad argument");
+    if (pl->outRank != 0) return fail(QTB_ERR_INVALID, "slot sums need a scalar plan output");
+    for (int j = 0; j < n; j++)
+        if (slots[j] < 0 || (size_t)slots[j] >= pl->slotDev.size() || !pl->slotDev[slots[j]]) return fail(QTB_ERR_INVALID, "unknown input slot");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ST(ensure_device(ctx));
+    ST(flush_locked(ctx));
+    const size_t nSegs = pl->segs.size(), pre = pl->prefixSegs;
+    const bool useGraph = plan_graphs_enabled() && !ctx->trace;
+    if (useGraph && !pl->partGraphsTried) {
+        pl->partGraphsTried = true;
+        if (pre >= 2) pl->graphPrefix = plan_capture(ctx, pl, 0, pre);
+        if (nSegs - pre >= 2) pl->graphSuffix = plan_capture(ctx, pl, pre, nSegs);
+    }
+    if ((size_t)n > ctx->batchOutCap) {
+        if (ctx->batchOut) cudaFreeHost(ctx->batchOut);
+        ctx->batchOutCap = std::max<size_t>(256, (size_t)n * 2);
+        CU(cudaMallocHost((void **)&ctx->batchOut, ctx->batchOutCap * 16));
+    }
+    for (int j = 0; j < n; j++) {
+        CU(cudaMemcpyAsync(pl->inBlobDev, pl->slotDev[slots[j]], pl->inBlobBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (j == 0 && pre > 0) {
+            // slot-invariant steps: once per call, from the first slot's copy of the (shared) inputs
+            if (useGraph && pl->graphPrefix) { CU(cudaGraphLaunch(pl->graphPrefix, ctx->stream)); ctx->stats.launches += pl->launchesPrefix; }
+            else ST(plan_enqueue(ctx, pl, ctx->stream, 0, pre));
+        }
+        if (useGraph && pl->graphSuffix) { CU(cudaGraphLaunch(pl->graphSuffix, ctx->stream)); ctx->stats.launches += pl->launches - pl->launchesPrefix; }
+        else ST(plan_enqueue(ctx, pl, ctx->stream, pre, nSegs));
+        CU(cudaMemcpyAsync(ctx->batchOut + 2 * j, pl->outDev, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    double sr = 0.0, si = 0.0;
+    for (int j = 0; j < n; j++) {
+        sr += ctx->batchOut[2 * j]; si += ctx->batchOut[2 * j + 1];
+        if (hostEach) { hostEach[2 * j] = ctx->batchOut[2 * j]; hostEach[2 * j + 1] = ctx->batchOut[2 * j + 1]; }
+    }
+    hostSum[0] = sr; hostSum[1] = si;
+    // work actually done: the prefix once, the suffix n times
+    long long preUnits = 0; int preSteps = 0, preMicro = 0;
+    for (size_t si2 = 0; si2 < pre; si2++) {
+        const PlanSeg &sg = pl->segs[si2];
+        preSteps += sg.nSteps;
+        if (sg.micro) preMicro += sg.nSteps;
+    }
+    preUnits = pl->prefixUnits;
+    ctx->stats.steps += preSteps + (long long)n * (pl->nSteps - preSteps);
+    ctx->stats.micro_steps += preMicro + (long long)n * (pl->nMicroSteps - preMicro);
+    ctx->stats.units += preUnits + (long long)n * (pl->units - preUnits);
+    ctx->stats.bytes_d2h += (long long)n * 16;
+    return QTB_OK;
+}
+long long qtb_plan_prefix_units(qtb_plan *pl) { return pl ? pl->prefixUnits : 0; }
 int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const double *const *const *hostInputs, double *hostOut) {
     if (!ctx || !plans || n < 1 || !hostInputs || !hostOut) return fail(QTB_ERR_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);

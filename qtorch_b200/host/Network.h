@@ -95,6 +95,10 @@ public:
     // ---- additions (not in the reference) -------------------------------------------------------------
     const std::vector<PlanRecord> &GetPlan() const noexcept { return mPlan; }     // every executed step, in order
     int GetNumOriginalNodes() const noexcept { return mNumOriginalNodes; }          // nodes created by the parser
+    // start the device->host read of the final scalar behind the steps enqueued so far, without waiting for it; a later
+    // GetFinalValue() then waits for that copy only.  Lets a caller enqueue the next network while this one still runs.
+    void PrefetchFinalValue();
+    ~Network() { DropPendingRead(); }
 
 private:
     std::vector<std::shared_ptr<Node>> mNetworkParsingNodes;
@@ -102,6 +106,10 @@ private:
     std::string mInputFile, mMeasureFile;
     std::complex<double> mFinalVal{std::complex<double>(0.0)};
     std::shared_ptr<Node> mFinalSource;                        // rank-0 node whose scalar still has to be read back
+    qtb_scalar_read *mFinalRead{nullptr};                      // ... or whose read-back is already in flight (PrefetchFinalValue)
+    void DropPendingRead() noexcept {
+        if (mFinalRead) { qtb_read_scalar_end(device::Engine::Get().ctx(), mFinalRead, nullptr); mFinalRead = nullptr; }
+    }
     std::mutex mLocker;
     int mNumberOfQubits{0};
     int mDepth{0};
@@ -148,6 +156,7 @@ inline void Network::Reset() {
     mNetworkParsingWires.clear();
     mFinalVal = std::complex<double>(0.0);
     mFinalSource.reset();
+    DropPendingRead();
     mNumberOfQubits = 0;
     mDepth = 0;
     mDone = false;
@@ -482,7 +491,20 @@ inline void Network::ContractIndices(const std::vector<std::pair<bool, int>> &to
     }
 }
 
+inline void Network::PrefetchFinalValue() {
+    if (!mFinalSource || mFinalRead || device::Engine::PlanOnly() || !mFinalSource->OnDevice()) return;
+    device::check(qtb_read_scalar_begin(device::Engine::Get().ctx(), mFinalSource->DeviceTensor(), &mFinalRead));
+    mFinalSource.reset();
+}
+
 inline void Network::ResolveFinalValue() {
+    if (mFinalRead) {
+        double v[2] = {0.0, 0.0};
+        qtb_scalar_read *r = mFinalRead;
+        mFinalRead = nullptr;
+        device::check(qtb_read_scalar_end(device::Engine::Get().ctx(), r, v));
+        mFinalVal = std::complex<double>(v[0], v[1]);
+    }
     if (!mFinalSource) return;
     std::shared_ptr<Node> src;
     src.swap(mFinalSource);

@@ -35,6 +35,9 @@ def host_library():
         H.qth_engine_ctx.restype = ctypes.c_void_p
         cd, cll, ci = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)
         H.qth_contract_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, cd, cll, ci, cd]
+        H.qth_linegraph_begin.restype = ctypes.c_void_p
+        H.qth_linegraph_begin.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+        H.qth_linegraph_end.argtypes = [ctypes.c_void_p, cd, cll, ci]
         H.qth_contract_sequence.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ctypes.c_int, cd, cll, ci, cd]
         H.qth_export_plan_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_QthPlan)]
         H.qth_maxcut_circuit_text.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, cd, ctypes.c_char_p, ctypes.c_int, ci, ci]
@@ -142,6 +145,36 @@ def contract_linegraph(qasm, measure, ordering, reduce=True):
     if rc != 0:
         _raise(H, rc)
     return complex(v[0], v[1]), flops.value, nodes.value, secs.value
+
+
+class LinegraphJob:
+    """contract_linegraph split in two: the constructor parses, reduces, walks the ordering and enqueues every step on
+    the device without synchronising; ``result()`` reads the scalar back.  Starting job i+1 before asking for the
+    result of job i hides the host bookkeeping of one network behind the device work of the previous one."""
+
+    def __init__(self, qasm, measure, ordering, reduce=True):
+        self.H = host_library()
+        self.h = self.H.qth_linegraph_begin(qasm.encode(), measure.encode(), ordering.encode(), 1 if reduce else 0)
+        if not self.h:
+            _raise(self.H, 1)
+
+    def result(self):
+        """-> (value, float ops, nodes); the job is consumed"""
+        if not self.h:
+            raise RuntimeError("job already consumed")
+        v = (ctypes.c_double * 2)()
+        flops, nodes = ctypes.c_longlong(), ctypes.c_int()
+        h, self.h = self.h, None
+        rc = self.H.qth_linegraph_end(h, v, ctypes.byref(flops), ctypes.byref(nodes))
+        if rc != 0:
+            _raise(self.H, rc)
+        return complex(v[0], v[1]), flops.value, nodes.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            v = (ctypes.c_double * 2)()
+            self.H.qth_linegraph_end(self.h, v, None, None)
+            self.h = None
 
 
 def contract_sequence(qasm, measure, pairs):

@@ -3,8 +3,9 @@
 The reference has no slicing (its only scale knobs are threads and ordering quality); this is the
 B200-side answer to "a network whose largest tensor does not fit, or that should spread over several GPUs": fixing the
 value d in {0,1,2,3} of s wires turns every tensor that carries such a wire into its d-slice (rank - 1), leaves the plan's
-step ORDER untouched (so the unsliced plan stays the reference's plan, bit for bit) and the network value becomes the sum
-of the 4^s sliced values.  All slices share one compiled device plan; only the (small) input tensors differ, so they are
+pairwise steps untouched (so the unsliced plan stays the reference's plan, bit for bit) and the network value becomes the
+sum of the 4^s sliced values.  Steps that no cut wire reaches are the same in every slice: hoist_invariant moves them to
+the front of the plan and the device runs them once per amplitude instead of once per slice.  All slices share one compiled device plan; only the (small) input tensors differ, so they are
 staged as input slots (qtb_plan_stage_inputs) and dealt round-robin to ranks by qtorch_b200.dispatch.
 
 A plan is (input_ranks, steps) with steps = [(a, b, posA, posB)] in the reference's mCreatedFrom numbering.
@@ -108,6 +109,28 @@ def slice_plan(input_ranks, steps, wires):
     return new_ranks, new_steps, {t: sorted(c) for t, c in cuts.items()}
 
 
+def hoist_invariant(n_inputs, steps, variant_inputs):
+    """Stable re-ordering of a plan: the steps that do not depend (transitively) on any tensor in `variant_inputs`
+    first, the dependent ones after them, tensor ids renumbered accordingly.  Every step is still the same pairwise
+    contraction of the same operands - only independent steps swap places - so the values are bit-identical; the
+    invariant prefix is what all slices of a network share (qtb_plan_create_sliced runs it once per amplitude).
+    Returns (steps', n_invariant_steps)."""
+    dep = set(variant_inputs)
+    order_inv, order_dep = [], []
+    for i, (a, b, _, _) in enumerate(steps):
+        if a in dep or b in dep:
+            dep.add(n_inputs + i)
+            order_dep.append(i)
+        else:
+            order_inv.append(i)
+    order = order_inv + order_dep
+    new_id = {t: t for t in range(n_inputs)}
+    for pos, i in enumerate(order):
+        new_id[n_inputs + i] = n_inputs + pos
+    out = [(new_id[steps[i][0]], new_id[steps[i][1]], list(steps[i][2]), list(steps[i][3])) for i in order]
+    return out, len(order_inv)
+
+
 def slice_inputs(inputs, input_ranks, cuts, wires, digits):
     """input tensors of the slice in which wire wires[i] carries digit digits[i]"""
     value = dict(zip(wires, digits))
@@ -128,24 +151,28 @@ def all_slices(wires):
     return list(itertools.product(range(4), repeat=len(wires)))
 
 
+def compile_sliced(engine, input_ranks, steps, wires):
+    """One device plan for all slices: sliced legs dropped, slice-invariant steps hoisted into a run-once prefix.
+    Returns (plan, cuts, n_invariant_steps)."""
+    ranks2, steps2, cuts = slice_plan(input_ranks, steps, wires)
+    steps3, n_inv = hoist_invariant(len(ranks2), steps2, cuts.keys())
+    return engine.plan(ranks2, steps3, invariant_steps=n_inv), cuts, n_inv
+
+
 def contract_sliced(engine, input_ranks, steps, inputs, wires, dispatcher=None):
-    """Sum over the 4^s slices on the device: one compiled plan, every owned slice staged as an input slot."""
+    """Sum over the 4^s slices on the device: one compiled plan, every owned slice staged as an input slot; the steps no
+    cut wire reaches run once, the others once per owned slice, partial sums meet in one allreduce."""
     from .dispatch import Dispatcher
     dispatcher = dispatcher or Dispatcher()
-    ranks2, steps2, cuts = slice_plan(input_ranks, steps, wires)
-    plan = engine.plan(ranks2, steps2)
+    plan, cuts, n_inv = compile_sliced(engine, input_ranks, steps, wires)
     slices = all_slices(wires)
     owned = dispatcher.owned(len(slices))
     for slot, u in enumerate(owned):
         plan.stage_inputs(slot, slice_inputs(inputs, input_ranks, cuts, wires, slices[u]))
-    slot_of = {u: s for s, u in enumerate(owned)}
-
-    def evaluate(u):
-        plan.run_device_slot(slot_of[u])
-        return complex(plan.read_output()[0])
-
-    total = dispatcher.map_reduce(len(slices), evaluate)
-    info = {"slices": len(slices), "owned": len(owned), "units_per_slice": plan.units, "launches_per_slice": plan.launches,
+    partial = plan.run_slots(range(len(owned))) if owned else 0.0 + 0.0j
+    total = dispatcher.map_reduce(dispatcher.world, lambda u: partial)      # one partial per rank, one allreduce
+    info = {"slices": len(slices), "owned": len(owned), "units_per_slice": plan.units - plan.prefix_units,
+            "units_shared": plan.prefix_units, "invariant_steps": n_inv, "launches_per_slice": plan.launches,
             "peak_rank": plan_cost(input_ranks, steps, frozenset(wires))[1]}
     plan.destroy()
     return total, info

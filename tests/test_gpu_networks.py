@@ -153,3 +153,24 @@ def test_in_process_minfill_ordering_gives_the_reference_value(built, name, tmp_
     assert _close(val, rec["value"]), (val, rec["value"])
     if name == "qaoa30_z27z29":
         assert int(out["flops"][0]) < rec["flops"]          # 2.2e10 vs QuickBB's 6.9e10 units
+
+
+def test_linegraph_jobs_in_flight_match_the_blocking_call(built):
+    """host_api.LinegraphJob (begin: parse + enqueue, no sync; result(): read back) with several networks in flight
+    gives exactly what the blocking contract_linegraph gives, whatever order the results are collected in."""
+    from qtorch_b200 import host_api
+    names = ["qft8_X8", "qaoa20_node1_m125", "testJW_YXXY", "qft8_X8"]
+    recs = [NETS[n] for n in names]
+    paths = []
+    for rec in recs:
+        cwd, qasm, meas, ordering = golden_paths(rec)
+        paths.append((os.path.join(cwd, qasm), meas if os.path.isabs(meas) else os.path.join(cwd, meas),
+                      ordering if os.path.isabs(ordering) else os.path.join(cwd, ordering), bool(rec["reduce"])))
+    blocking = [host_api.contract_linegraph(*p) for p in paths]
+    jobs = [host_api.LinegraphJob(*p) for p in paths]
+    for i in (2, 0, 3, 1):
+        v, flops, nodes = jobs[i].result()
+        assert abs(v - blocking[i][0]) <= 1e-14 and flops == blocking[i][1] == recs[i]["flops"] and nodes == blocking[i][2]
+        assert _close(v, recs[i]["value"])
+    with pytest.raises(RuntimeError):
+        jobs[0].result()

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "fused or config2 or plan_api or random_leg or qaoa30" 2>&1 | tail -8 | tee gpurun_out/try.log
-QTB_GETT_C1=1 timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "fused or config2" 2>&1 | tail -3 | tee -a gpurun_out/try.log
+timeout 600 python -m pytest tests/test_slicing.py tests/test_gpu_networks.py -x -q -m gpu --timeout 300 -k "slic or run_slots or jobs_in_flight or value_matches" 2>&1 | tail -8 | tee gpurun_out/try.log
+timeout 300 python tools/prof_e2e.py 2>&1 | tee gpurun_out/prof_e2e.log
 timeout 600 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_try.log
 python - <<PY
 import json
