@@ -125,6 +125,78 @@ __global__ void __launch_bounds__(512) v5(const double2 *in, double *out, int it
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// v6: v5 with the re+im sums issued back to back (asm volatile keeps program order), GROUP = how many k-steps' worth of
+// sums are computed in one burst (1: 4 DADDs then 12 DMMAs; 4: 16 DADDs then 48 DMMAs) -- is the ~4.7-cycle cost of a DADD
+// next to DMMAs a pipe turn-around that batching amortises?
+__device__ __forceinline__ double dadd_v(double a, double b) { double r; asm volatile("add.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b)); return r; }
+template <int GROUP>
+__global__ void __launch_bounds__(512) v6(const double2 *in, double *out, int iters) {
+    constexpr int FX = 2, FY = 2;
+    extern __shared__ double2 sm[];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = in[i];
+    __syncthreads();
+    double c1[FX][FY][2], c2[FX][FY][2], c3[FX][FY][2];
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = c3[i][j][0] = c3[i][j][1] = 0;
+    for (int it = 0; it < iters; it += GROUP) {
+        double2 xf[GROUP][FX], yf[GROUP][FY];
+        double xs[GROUP][FX], ys[GROUP][FY];
+#pragma unroll
+        for (int u = 0; u < GROUP; u++) {
+            const int kk = (it + u) & 3;
+#pragma unroll
+            for (int i = 0; i < FX; i++) xf[u][i] = sm[(kk * 4 + t) * 66 + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < FY; j++) yf[u][j] = sm[2100 + (kk * 4 + t) * 66 + j * 8 + g];
+        }
+#pragma unroll
+        for (int u = 0; u < GROUP; u++) {
+#pragma unroll
+            for (int i = 0; i < FX; i++) xs[u][i] = dadd_v(xf[u][i].x, xf[u][i].y);
+#pragma unroll
+            for (int j = 0; j < FY; j++) ys[u][j] = dadd_v(yf[u][j].x, yf[u][j].y);
+        }
+        __syncwarp();                                   // scheduling fence: keeps the DADD burst together in SASS
+#pragma unroll
+        for (int u = 0; u < GROUP; u++) {
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(c1[i][j][0], c1[i][j][1], xf[u][i].x, yf[u][j].x);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(c2[i][j][0], c2[i][j][1], xf[u][i].y, yf[u][j].y);
+#pragma unroll
+            for (int i = 0; i < FX; i++)
+#pragma unroll
+                for (int j = 0; j < FY; j++) dmma(c3[i][j][0], c3[i][j][1], xs[u][i], ys[u][j]);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < FX; i++) for (int j = 0; j < FY; j++) s += c1[i][j][0] + c1[i][j][1] + c2[i][j][0] + c2[i][j][1] + c3[i][j][0] + c3[i][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// v7: how fast is a stream of DADDs alone / DADD:DMMA mixes from ONE warp per scheduler vs four (R DADDs per DMMA)
+template <int R>
+__global__ void __launch_bounds__(512) v7(const double *in, double *out, int iters) {
+    double a = in[threadIdx.x], b = in[threadIdx.x + 512];
+    double c0 = 0, c1 = 0, e[8];
+    for (int i = 0; i < 8; i++) e[i] = in[threadIdx.x + 32 * i];
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            dmma(c0, c1, a, b);
+#pragma unroll
+            for (int q = 0; q < R; q++) e[(r * R + q) & 7] = dadd_v(e[(r * R + q) & 7], a);
+        }
+    }
+    double s = c0 + c1;
+    for (int i = 0; i < 8; i++) s += e[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static float time_ms(F f) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -160,5 +232,20 @@ int main() {
     RUN5(2, 2, 0, "v5_3M_2x2_LDS_noDADD");
     RUN5(4, 2, 1, "v5_3M_4x2_LDS_DADD");
     RUN5(4, 2, 0, "v5_3M_4x2_LDS_noDADD");
+#define RUN6(G, NAME) \
+    CK(cudaFuncSetAttribute(v6<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    for (int w : {8, 16}) { float ms = time_ms([&] { v6<G><<<nsm, w * 32, smem>>>((const double2 *)in, out, iters); }); rep(NAME, w, 12, ms); }
+    RUN6(1, "v6_3M_2x2_sums_burst_of_4");
+    RUN6(2, "v6_3M_2x2_sums_burst_of_8");
+    RUN6(4, "v6_3M_2x2_sums_burst_of_16");
+    // v7: 4 DMMAs + 4R DADDs per iteration; report the time per iteration in SM cycles per scheduler-warp
+    auto rep7 = [&](const char *name, int warps, int R, float ms) {
+        double cyc = ms * 1e-3 * 1.965e9 / iters;          // cycles per iteration (4 DMMA + 4R DADD per warp)
+        printf("{\"probe\":\"%s\",\"warps_per_sm\":%d,\"dadd_per_dmma\":%d,\"cycles_per_iter\":%.1f,\"ms\":%.3f}\n", name, warps, R, cyc, ms);
+    };
+    for (int w : {4, 16}) { float ms = time_ms([&] { v7<0><<<nsm, w * 32>>>(in, out, iters); }); rep7("v7_dmma_only", w, 0, ms); }
+    for (int w : {4, 16}) { float ms = time_ms([&] { v7<1><<<nsm, w * 32>>>(in, out, iters); }); rep7("v7_dmma_dadd", w, 1, ms); }
+    for (int w : {4, 16}) { float ms = time_ms([&] { v7<2><<<nsm, w * 32>>>(in, out, iters); }); rep7("v7_dmma_dadd", w, 2, ms); }
+    for (int w : {4, 16}) { float ms = time_ms([&] { v7<4><<<nsm, w * 32>>>(in, out, iters); }); rep7("v7_dmma_dadd", w, 4, ms); }
     return 0;
 }
