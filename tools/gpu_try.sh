@@ -1,12 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "fused or config2 or plan_api or random_leg or qaoa30 or step" 2>&1 | tail -5 | tee gpurun_out/try.log
-for v in 2 3; do
-echo "== QTB_GETT_C1=$v" | tee -a gpurun_out/try.log
-QTB_GETT_C1=$v timeout 120 python tools/prof_step.py 10 10 3 7 8 9 0 1 2 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
-QTB_GETT_C1=$v timeout 120 python tools/prof_step.py 9 11 3 0 4 8 2 5 9 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
-QTB_GETT_C1=$v timeout 120 python tools/prof_step.py 6 14 3 1 3 5 0 6 12 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "presummed or fused or config2 or plan_api or random_leg or qaoa30 or gett" 2>&1 | tail -5 | tee gpurun_out/try.log
+for v in "QTB_PRESUM=0" "QTB_PRESUM=1" "QTB_PRESUM_TK8=1"; do
+echo "== $v" | tee -a gpurun_out/try.log
+env $v timeout 120 python tools/prof_step.py 10 10 3 7 8 9 0 1 2 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
+env $v timeout 120 python tools/prof_step.py 9 11 3 0 4 8 2 5 9 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
+env $v timeout 120 python tools/prof_step.py 6 14 3 1 3 5 0 6 12 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
+env $v timeout 120 python tools/prof_step.py 9 9 3 1 3 5 0 6 8 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
 done
 timeout 600 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_try.log
 python - <<PY
