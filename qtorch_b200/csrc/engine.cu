@@ -361,6 +361,10 @@ struct qtb_ctx_s {
     std::vector<qtb_scalar_read_s *> freeReads;   // recycled handles of qtb_read_scalar_begin/end
     uint64_t *zeroOffsetDev = nullptr;          // blobOffsets[0] = 0 for single-blob launches
     double2 *reduceScratch = nullptr;           // split-K partials: [REDUCE_MAX_BLOCKS][16]
+    double2 *scratchOverride = nullptr;         // a plan's private partials while its launches are enqueued (plans may run side by side)
+    double2 *partials() const { return scratchOverride ? scratchOverride : reduceScratch; }
+    // fork/join streams for independent plans (qtb_plans_run_batched)
+    std::vector<cudaStream_t> auxStreams; std::vector<cudaEvent_t> auxEvents; cudaEvent_t forkEvent = nullptr;
     // deferred micro work
     std::vector<PendingStep> pending;
     std::vector<PendingUpload> pendingUploads;
@@ -401,12 +405,12 @@ static int launch_gett(qtb_ctx *ctx, const GettParams &p, int cfg, cudaStream_t 
 static const unsigned REDUCE_MAX_BLOCKS = 148 * 8;
 static int launch_reduce(qtb_ctx *ctx, const StepGeom &g, const double2 *A, const double2 *B, double2 *C, cudaStream_t s) {
     ReduceParams p;
-    build_reduce(g, A, B, C, ctx->reduceScratch, p);
+    build_reduce(g, A, B, C, ctx->partials(), p);
     if (g.rC == 0) {
         // inner product: each operand streamed in its own memory order, permutation undone in shared memory
         DotParams d;
         memset(&d, 0, sizeof(d));
-        d.A = A; d.B = B; d.partial = ctx->reduceScratch; d.nTiles = p.nTiles; d.kbits = p.kbits;
+        d.A = A; d.B = B; d.partial = ctx->partials(); d.nTiles = p.nTiles; d.kbits = p.kbits;
         memcpy(d.shA, p.shA, 32); memcpy(d.shB, p.shB, 32);
         int ia[8], ib[8];
         for (int j = 0; j < 8; j++) ia[j] = ib[j] = j;
@@ -415,7 +419,7 @@ static int launch_reduce(qtb_ctx *ctx, const StepGeom &g, const double2 *A, cons
         for (int j = 0; j < 8; j++) { d.permA[j] = (uint8_t)ia[j]; d.permB[j] = (uint8_t)ib[j]; }
         const unsigned grid = std::min<unsigned>((p.nTiles + QTB_DOT_T - 1) / QTB_DOT_T, std::min<unsigned>(REDUCE_MAX_BLOCKS, (unsigned)ctx->numSMs * 6));
         k_dot<<<grid, 256, 0, s>>>(d);
-        k_reduce_final<1><<<1, 32, 0, s>>>(ctx->reduceScratch, C, grid);
+        k_reduce_final<1><<<1, 32, 0, s>>>(ctx->partials(), C, grid);
         CU(cudaGetLastError());
         ctx->stats.launches += 2;
         return QTB_OK;
@@ -582,11 +586,11 @@ static int enqueue_fused(qtb_ctx *ctx, const StepGeom &g1, const GettChoice &gc1
     build_gett(g1, gc1, A1, B1, nullptr, p);
     const int cfg = fused_variant_of(gc1.cfg);
     const GettInst &inst = g_gett[cfg];
-    add_fusion(g2, tIsA, D, ctx->reduceScratch, inst, p);
+    add_fusion(g2, tIsA, D, ctx->partials(), inst, p);
     const unsigned nTiles = p.nTilesX * p.nTilesY;
     const unsigned grid = std::min<unsigned>(nTiles, (unsigned)(ctx->numSMs * inst.occ));
     inst.fn<<<grid, inst.NT, inst.smem, s>>>(p);
-    k_reduce_final<1><<<1, 32, 0, s>>>(ctx->reduceScratch, out, grid);
+    k_reduce_final<1><<<1, 32, 0, s>>>(ctx->partials(), out, grid);
     CU(cudaGetLastError());
     ctx->stats.launches += 2;
     return QTB_OK;
@@ -677,6 +681,9 @@ int qtb_ctx_destroy(qtb_ctx *ctx) {
     if (ctx->commBuf) cudaFree(ctx->commBuf);
     for (auto &t : ctx->traceRecs) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     ctx->pool.destroy();
+    for (cudaStream_t a : ctx->auxStreams) cudaStreamDestroy(a);
+    for (cudaEvent_t e : ctx->auxEvents) cudaEventDestroy(e);
+    if (ctx->forkEvent) cudaEventDestroy(ctx->forkEvent);
     for (qtb_scalar_read_s *r : ctx->freeReads) { cudaFreeHost(r->pinned); cudaEventDestroy(r->done); delete r; }
     cudaFreeHost(ctx->ringHost); cudaFree(ctx->ringDev); cudaFreeHost(ctx->scalarPinned); cudaFree(ctx->zeroOffsetDev); cudaFree(ctx->reduceScratch);
     cudaEventDestroy(ctx->ringEvent);

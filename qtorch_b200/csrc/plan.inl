@@ -31,6 +31,7 @@ struct qtb_plan_s {
     long long units = 0; int nSteps = 0, nMicroSteps = 0; int launches = 0;
     cudaGraphExec_t graph = nullptr; bool graphTried = false;
     std::vector<uint8_t *> slotDev;          // extra resident copies of the small-input blob
+    double2 *partialsDev = nullptr;          // private split-K / fused-dot partials (plans of one batch run on parallel streams)
     // slot-invariant prefix (qtb_plan_create_sliced): segs[0..prefixSegs) do not depend on the inputs that differ between
     // slots, so qtb_plan_run_slots runs them once and only segs[prefixSegs..) per slot; their results stay live.
     int nPrefixSteps = 0; size_t prefixSegs = 0; int launchesPrefix = 0; long long prefixUnits = 0;
@@ -45,6 +46,11 @@ static bool plan_graphs_enabled() {
 
 static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s, size_t segBegin = 0, size_t segEnd = (size_t)-1) {
     if (segEnd > pl->segs.size()) segEnd = pl->segs.size();
+    struct ScratchScope {                      // launches of this plan write their partial sums into the plan's own buffer
+        qtb_ctx *c; double2 *saved;
+        ScratchScope(qtb_ctx *ctx, double2 *p) : c(ctx), saved(ctx->scratchOverride) { if (p) c->scratchOverride = p; }
+        ~ScratchScope() { c->scratchOverride = saved; }
+    } scope(ctx, pl->partialsDev);
     for (size_t si = segBegin; si < segEnd; si++) {
         const PlanSeg &sg = pl->segs[si];
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -102,6 +108,7 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int
     }
     qtb_plan *pl = new qtb_plan_s();
     auto bail = [&](int st) { pl->pool.destroy(); if (pl->inBlobHost) cudaFreeHost(pl->inBlobHost); if (pl->inBlobDev) cudaFree(pl->inBlobDev);
+                              if (pl->partialsDev) cudaFree(pl->partialsDev);
                               if (pl->microBlobDev) cudaFree(pl->microBlobDev); if (pl->segOffsetsDev) cudaFree(pl->segOffsetsDev); delete pl; return st; };
     pl->nInputs = nInputs; pl->inputRanks.assign(inputRanks, inputRanks + nInputs);
     pl->inputDev.assign(nInputs, nullptr); pl->inputBlobOff.assign(nInputs, (size_t)-1);
@@ -224,6 +231,10 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int
             return bail(fail(QTB_ERR_CUDA, "plan blob upload failed"));
     }
     if (cudaEventCreateWithFlags(&pl->inEvent, cudaEventDisableTiming) != cudaSuccess) return bail(fail(QTB_ERR_CUDA, "event"));
+    for (const PlanSeg &sg : pl->segs)
+        if (!sg.micro && (sg.kind == KIND_REDUCE || sg.fused) && !pl->partialsDev &&
+            cudaMalloc((void **)&pl->partialsDev, (size_t)REDUCE_MAX_BLOCKS * 16 * sizeof(double2)) != cudaSuccess)
+            return bail(fail(QTB_ERR_OOM, "plan partial-sum buffer allocation failed"));
     *out = pl;
     return QTB_OK;
 }
@@ -243,6 +254,7 @@ int qtb_plan_destroy(qtb_ctx *ctx, qtb_plan *pl) {
     if (pl->microBlobDev) cudaFree(pl->microBlobDev);
     if (pl->segOffsetsDev) cudaFree(pl->segOffsetsDev);
     if (pl->inEvent) cudaEventDestroy(pl->inEvent);
+    if (pl->partialsDev) cudaFree(pl->partialsDev);
     for (uint8_t *p : pl->slotDev) if (p) cudaFree(p);
     delete pl;
     return QTB_OK;
@@ -284,19 +296,20 @@ static cudaGraphExec_t plan_capture(qtb_ctx *ctx, qtb_plan *pl, size_t segBegin,
     return exec;
 }
 
-static int plan_run_locked(qtb_ctx *ctx, qtb_plan *pl) {
+static int plan_run_locked(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t stream = nullptr) {
     ST(ensure_device(ctx));
     ST(flush_locked(ctx));
+    if (!stream) stream = ctx->stream;
     const bool useGraph = plan_graphs_enabled() && !ctx->trace && pl->segs.size() >= 3;
     if (useGraph && !pl->graphTried) {
         pl->graphTried = true;
         pl->graph = plan_capture(ctx, pl, 0, pl->segs.size());
     }
     if (useGraph && pl->graph) {
-        CU(cudaGraphLaunch(pl->graph, ctx->stream));
+        CU(cudaGraphLaunch(pl->graph, stream));
         ctx->stats.launches += pl->launches;
     } else {
-        ST(plan_enqueue(ctx, pl, ctx->stream));
+        ST(plan_enqueue(ctx, pl, stream));
     }
     ctx->stats.steps += pl->nSteps;
     ctx->stats.micro_steps += pl->nMicroSteps;
@@ -443,8 +456,33 @@ int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const dou
         ctx->ringEventValid = true;
         ctx->stats.launches++;
         for (int i = 0; i < n; i++) { ctx->stats.steps += plans[i]->nSteps; ctx->stats.micro_steps += plans[i]->nMicroSteps; ctx->stats.units += plans[i]->units; }
-    } else {
+    } else if (ctx->trace || n == 1) {
         for (int i = 0; i < n; i++) ST(plan_run_locked(ctx, plans[i]));
+    } else {
+        // independent plans with their own buffers: fork over side streams, join before the read-back.  Most of a small
+        // plan is one single-CTA grouped launch, so plans side by side fill the SMs that one plan leaves idle.
+        const int nAux = std::min(n, 16);
+        while ((int)ctx->auxStreams.size() < nAux) {
+            cudaStream_t a = nullptr; cudaEvent_t e = nullptr;
+            CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+            ctx->auxStreams.push_back(a);
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->auxEvents.push_back(e);
+        }
+        if (!ctx->forkEvent) CU(cudaEventCreateWithFlags(&ctx->forkEvent, cudaEventDisableTiming));
+        // graphs are captured on the main stream (first run only), before the fork
+        for (int i = 0; i < n; i++)
+            if (plan_graphs_enabled() && plans[i]->segs.size() >= 3 && !plans[i]->graphTried) {
+                plans[i]->graphTried = true;
+                plans[i]->graph = plan_capture(ctx, plans[i], 0, plans[i]->segs.size());
+            }
+        CU(cudaEventRecord(ctx->forkEvent, ctx->stream));
+        for (int a = 0; a < nAux; a++) CU(cudaStreamWaitEvent(ctx->auxStreams[a], ctx->forkEvent, 0));
+        for (int i = 0; i < n; i++) ST(plan_run_locked(ctx, plans[i], ctx->auxStreams[i % nAux]));
+        for (int a = 0; a < nAux; a++) {
+            CU(cudaEventRecord(ctx->auxEvents[a], ctx->auxStreams[a]));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->auxEvents[a], 0));
+        }
     }
     // gather the n scalars: n tiny async copies into pinned memory, one wait
     if ((size_t)n > ctx->batchOutCap) {

@@ -1,16 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "presummed or fused or config2 or plan_api or random_leg or qaoa30 or gett" 2>&1 | tail -5 | tee gpurun_out/try.log
-for v in "QTB_PRESUM=0" "QTB_PRESUM=1" "QTB_PRESUM_TK8=1"; do
-echo "== $v" | tee -a gpurun_out/try.log
-env $v timeout 120 python tools/prof_step.py 10 10 3 7 8 9 0 1 2 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
-env $v timeout 120 python tools/prof_step.py 9 11 3 0 4 8 2 5 9 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
-env $v timeout 120 python tools/prof_step.py 6 14 3 1 3 5 0 6 12 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
-env $v timeout 120 python tools/prof_step.py 9 9 3 1 3 5 0 6 8 3 2>&1 | tail -1 | tee -a gpurun_out/try.log
-done
-timeout 600 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_try.log
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench_try.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['config']['plan_launches_per_term'], d['kernel_time_ms_by_kind'], 'roof', d['roofline']['achieved'], 'sliced', d['sliced']['ms_per_amplitude'], d['sliced']['matches_reference_1e-10'], 'minfill', d['minfill_plan']['ms_per_term'], d['minfill_plan']['matches_reference_1e-10'])
-PY
+timeout 900 python -m pytest tests/test_maxcut.py tests/test_gpu_steps.py tests/test_gpu_networks.py -x -q -m gpu --timeout 600 -k "not drop_in" 2>&1 | tail -5 | tee gpurun_out/try.log
+timeout 600 python tools/bench_configs.py 2>&1 | grep maxcut | cut -c1-400 | tee gpurun_out/configs_try.jsonl
