@@ -21,6 +21,8 @@
 //   seq   qasm measure plan.txt threads [budget]    replay "(a b)" pairs via ContractNodes, per-step timing;
 //                                                   stops once `budget` units have been executed (bounded sample)
 //   stoch qasm measure threads                      ContractionTools::Contract(Stochastic), prints the plan
+//   cost  qasm measure pValue seed threads          ContractionTools::Contract(CostContractSimple, pValue) with the
+//                                                   generator seeded (see the access note below), prints the plan
 //   user  qasm measure seqfile                      ContractUserDefinedSequenceOfWires
 //   maxcut graph.dgf p outdir b1..bp g1..gp         the body of F_p (src/maxcut.cpp:162-204) for fixed angles: per-edge
 //                                                   light-cone circuits written with the reference's own emitters
@@ -33,7 +35,30 @@
 #include <complex>
 #include <chrono>
 
+// ContractionTools seeds its private std::mt19937 from std::random_device (src/ContractionTools.h:61,97), so its random
+// planners cannot be replayed.  To pin the host mirror's restatement of CostContractSimple draw by draw, the `cost` mode
+// assigns that generator a fixed seed; the access override below is the only liberty taken with the reference, it is
+// compile-time, confined to this test harness, and does not touch the sources (every standard header the reference
+// pulls in is included BEFORE the override so that only the reference's own classes are affected).
+#include <algorithm>
+#include <array>
+#include <csignal>
+#include <exception>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <random>
+#include <regex>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+#include <sys/stat.h>
+#define private public
 #include "ContractionTools.h"   // reference header (pulls Network.h, Node.h, LineGraph.h ...)
+#undef private
 #include "maxcut.h"             // reference QAOA helpers (ExtraData, circuit emitters); <nlopt.hpp> = oracle/stubs
 
 using namespace qtorch;
@@ -205,6 +230,18 @@ static int mode_stoch(int argc, char **argv) {
     return 0;
 }
 
+static int mode_cost(int argc, char **argv) {
+    const int pValue = atoi(argv[4]);
+    const unsigned seed = (unsigned)strtoul(argv[5], nullptr, 10);
+    ContractionTools p(argv[2], argv[3], argc > 6 ? atoi(argv[6]) : 8);
+    p.mRandGen = std::mt19937(seed);
+    auto net = p.Contract(CostContractSimple, pValue);
+    print_value("value", p.GetFinalVal());
+    printf("@@flops %lld\n", net->getNumFloatOps());
+    print_plan(net);
+    return 0;
+}
+
 static int mode_user(int argc, char **argv) {
     ContractionTools p(argv[2], argv[3]);
     auto net = p.ContractUserDefinedSequenceOfWires(argv[4]);
@@ -253,6 +290,7 @@ int main(int argc, char **argv) {
         if (m == "qbb") return mode_qbb(argc, argv);
         if (m == "seq") return mode_seq(argc, argv);
         if (m == "stoch") return mode_stoch(argc, argv);
+        if (m == "cost") return mode_cost(argc, argv);
         if (m == "user") return mode_user(argc, argv);
         if (m == "maxcut") return mode_maxcut(argc, argv);
     } catch (std::exception &e) {

@@ -151,6 +151,18 @@ static int mode_stoch(int argc, char **argv, bool steps) {
     return 0;
 }
 
+// cost qasm measure pValue seed: ContractionTools::Contract(CostContractSimple, pValue) with a fixed seed
+static int mode_cost(int argc, char **argv, bool steps) {
+    ContractionTools tools(argv[2], argv[3]);
+    tools.SetSeed((unsigned)strtoul(argv[5], nullptr, 10));
+    auto net = tools.Contract(CostContractSimple, atoi(argv[4]));
+    print_value("value", tools.GetFinalVal());
+    printf("@@flops %lld\n", net->getNumFloatOps());
+    print_plan(net);
+    if (steps) print_steps(net);
+    return 0;
+}
+
 static int mode_user(int argc, char **argv) {
     ContractionTools tools(argv[2], argv[3]);
     auto net = tools.ContractUserDefinedSequenceOfWires(argv[4]);
@@ -172,6 +184,7 @@ int main(int argc, char **argv) {
         if (m == "minfill") return mode_minfill(argc, argv, steps);
         if (m == "seq") return mode_seq(argc, argv, steps);
         if (m == "stoch") return mode_stoch(argc, argv, steps);
+        if (m == "cost") return mode_cost(argc, argv, steps);
         if (m == "user") return mode_user(argc, argv);
     } catch (std::exception &e) {
         printf("@@exception %s\n", e.what());

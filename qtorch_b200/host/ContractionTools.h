@@ -4,8 +4,11 @@
 // ContractNodes moved to the GPU.  Implemented: Stochastic (ParallelContract, reference :219-388),
 // FromEdges (:1072-1190), ContractGivenSequence (:392-411, the plan-replay entry),
 // ContractUserDefinedSequenceOfWires (:154-214), the reduce-and-print helpers (:1196-1229) and
-// CalculateTreewidth (:1232-1256).  The two cost-based searches (:431-899) are not part of the hot path and
-// are not provided yet: they throw InvalidContractionMethod.
+// CalculateTreewidth (:1232-1256) and the sampled greedy search CostContractSimple (:837-1046: draw ~log2(n) connected
+// pairs, score each by the 4^(rA+rB-k) cost of the step plus pValue randomly grown look-ahead steps, contract the
+// cheapest; rank / wire thresholds escalate when every draw is rejected).  With the same seed it draws the same random
+// numbers in the same order as the reference, so the plans coincide (tests/golden "cost" cases).  The multi-threaded
+// brute-force sampler (:431-835) is not on the hot path and is not provided: it throws InvalidContractionMethod.
 //
 // Addition: SetSeed() / QTORCH_SEED make the stochastic search reproducible (the reference seeds from
 // std::random_device, ContractionTools.h:61, so its plans cannot be replayed without recording them).
@@ -78,6 +81,14 @@ protected:
     void CreateChunksOfNodes(std::shared_ptr<Network> &myNetwork);
     std::shared_ptr<Network> ParallelContract(std::mt19937 &randomGenerator);
     std::shared_ptr<Network> ContractFromEdges(std::mt19937 &randomGenerator);
+    std::shared_ptr<Network> CostBasedContractionSimple(const int pValue);
+    long long CalculateCost(const int pVal, const int indexA, const int indexB, const int thresholdFinalRank, const int thresholdNumwires);
+    int NumberOfConnectedBetweenTwoSuperNodes(const std::vector<std::shared_ptr<Node>> &groupA, const std::vector<std::shared_ptr<Node>> &groupB) {
+        int n = 0;
+        for (const auto &a : groupA)
+            for (const auto &b : groupB) n += NumberOfConnectedWires(a, b);
+        return n;
+    }
     int NumberOfConnectedWires(std::shared_ptr<Node> nodeA, std::shared_ptr<Node> nodeB) {
         int n = 0;
         for (const auto &w : nodeA->GetWires())
@@ -87,10 +98,110 @@ protected:
 };
 
 inline std::shared_ptr<Network> ContractionTools::Contract(ContractionType type, int pValue, int numSamples) {
-    (void)pValue; (void)numSamples;
+    (void)numSamples;
     if (type == Stochastic) return ParallelContract(mRandGen);
     if (type == FromEdges) return ContractFromEdges(mRandGen);
-    throw InvalidContractionMethod();        // cost-based searches: not provided (see header comment)
+    if (type == CostContractSimple) return CostBasedContractionSimple(pValue);
+    throw InvalidContractionMethod();        // brute-force sampler: not provided (see header comment)
+}
+
+// ---- CostContractSimple (reference ContractionTools.h:837-899) ----------------------------------------
+// One step per round: about log2(#nodes) admissible random pairs are scored and the cheapest is contracted.
+// A draw is thrown away (and redrawn) when the two nodes are not connected, are the same node, or are the
+// pair currently held as best; a draw whose score is -1 (over the rank / wire thresholds) counts as a
+// failure, and more failures than nodes relax both thresholds by one.  The order of the random draws is
+// part of the plan identity, so the control flow below follows the reference statement by statement.
+inline std::shared_ptr<Network> ContractionTools::CostBasedContractionSimple(const int pValue) {
+    if (!mCopyCreated) mNetwork = OpenNetwork();
+    if (mNetwork->HasFailed()) return nullptr;
+    while (!mNetwork->IsDone() && totTimer.getElapsed() < maxTime) {
+        const auto &live = mNetwork->GetUncontractedNodes();
+        long long best = -1;
+        int pick[2] = {0, 1};
+        std::uniform_int_distribution<> draw(0, static_cast<int>(live.size()) - 1);
+        int rejected = 0, rankLimit = 11, wireLimit = 8;
+        if (live.size() != 2) {
+            for (int round = 0; round < std::log2(live.size()) && totTimer.getElapsed() < maxTime; round++) {
+                const int one = draw(mRandGen);
+                const int two = draw(mRandGen);
+                const bool heldPair = (pick[0] == one && pick[1] == two) || (pick[1] == one && pick[0] == two);
+                if (NumberOfConnectedWires(live[one], live[two]) == 0 || heldPair || one == two) { --round; continue; }
+                const long long score = CalculateCost(pValue, one, two, rankLimit, wireLimit);
+                if (score == -1) {
+                    ++rejected;
+                    --round;
+                    if (rejected > static_cast<int>(live.size())) { ++rankLimit; ++wireLimit; rejected = 0; }
+                    continue;
+                }
+                if (score < best || round == 0) { pick[0] = one; pick[1] = two; best = score; }
+            }
+        }
+        mNetwork->ContractNodes(live[pick[0]], live[pick[1]], 1000000);
+        if (!detail::quietMode()) std::cout << "Nodes Left: " << mNetwork->GetUncontractedNodes().size() << std::endl;
+    }
+    if (!mNetwork->IsDone()) throw ContractionFailure();
+    mFinalVal = mNetwork->GetFinalValue();
+    return mNetwork;
+}
+
+// Score of contracting live nodes indexA, indexB (reference ContractionTools.h:901-1046).
+//   pVal == 0: rank(A) + rank(B) - (wires between them).
+//   otherwise: -1 if the result rank exceeds thresholdFinalRank or more than thresholdNumwires wires connect the pair;
+//   else 4^(rA+rB-k) plus the cost of pVal further steps, each absorbing one randomly drawn neighbour of the growing
+//   super-node (a neighbour that would push the work exponent to >= 12 is redrawn up to 2*|neighbours| times).
+// The "selected" marks live on the nodes (Node::mSelectedInCostContractionAlgorithm) and the reference leaves them set
+// on its two early exits (no neighbours left / too many redraws); later calls see those marks, so the exits are kept.
+inline long long ContractionTools::CalculateCost(const int pVal, const int indexA, const int indexB, const int thresholdFinalRank,
+                                                 const int thresholdNumwires) {
+    const auto &live = mNetwork->GetUncontractedNodes();
+    const std::shared_ptr<Node> &a = live[indexA], &b = live[indexB];
+    int shared = NumberOfConnectedWires(a, b);
+    if (pVal == 0) return a->mRank + b->mRank - shared;
+    if (a->mRank + b->mRank - 2 * shared > thresholdFinalRank || shared > thresholdNumwires) return -1;
+
+    std::vector<std::shared_ptr<Node>> super, frontier;
+    // every unmarked node on the far side of one of n's wires joins the frontier (and gets marked)
+    auto growFrontier = [&frontier](const std::shared_ptr<Node> n) {       // by value: frontier may reallocate while n's wires are walked
+        for (const auto &w : n->GetWires()) {
+            const std::shared_ptr<Node> endA = w->GetNodeA().lock(), endB = w->GetNodeB().lock();
+            if (endA->mSelectedInCostContractionAlgorithm && endB->mSelectedInCostContractionAlgorithm) continue;
+            const std::shared_ptr<Node> &fresh = endA->mSelectedInCostContractionAlgorithm ? endB : endA;
+            fresh->mSelectedInCostContractionAlgorithm = true;
+            frontier.push_back(fresh);
+        }
+    };
+    long long cost = static_cast<long long>(std::pow(4, a->mRank + b->mRank - shared));
+    int superRank = a->mRank + b->mRank - 2 * shared;
+    super.push_back(a); a->mSelectedInCostContractionAlgorithm = true;
+    super.push_back(b); b->mSelectedInCostContractionAlgorithm = true;
+    growFrontier(a);
+    growFrontier(b);
+    int redraws = 0;
+    for (int step = 0; step < pVal; step++) {
+        if (frontier.empty()) return cost;                                     // (marks stay set, as in the reference)
+        std::uniform_int_distribution<> draw(0, static_cast<int>(frontier.size()) - 1);
+        // slots of absorbed neighbours are empty.  Deviation: when EVERY slot is empty (the super-node has swallowed its
+        // whole neighbourhood, typical for pValue >= 2) the reference redraws forever (:1002-1004); stop looking ahead.
+        if (std::all_of(frontier.begin(), frontier.end(), [](const std::shared_ptr<Node> &n) { return n == nullptr; })) break;
+        int r = draw(mRandGen);
+        while (frontier[r] == nullptr) r = draw(mRandGen);
+        shared = NumberOfConnectedBetweenTwoSuperNodes(super, {frontier[r]});
+        if (superRank + frontier[r]->mRank - shared >= 12 && redraws < static_cast<int>(frontier.size()) * 2) {
+            ++redraws;
+            --step;
+            continue;
+        }
+        if (redraws > static_cast<int>(frontier.size()) * 2) return -1;        // (marks stay set, as in the reference)
+        redraws = 0;
+        cost += std::pow(4, superRank) * std::pow(4, frontier[r]->mRank) / std::pow(4, shared);
+        superRank += frontier[r]->mRank - 2 * shared;
+        growFrontier(frontier[r]);
+        super.push_back(std::move(frontier[r]));
+    }
+    for (auto &n : super) n->mSelectedInCostContractionAlgorithm = false;
+    for (auto &n : frontier)
+        if (n != nullptr) n->mSelectedInCostContractionAlgorithm = false;
+    return cost;
 }
 
 // remove the two operands (positions one, two) from a working list the way the reference does -- the

@@ -174,3 +174,18 @@ def test_linegraph_jobs_in_flight_match_the_blocking_call(built):
         assert _close(v, recs[i]["value"])
     with pytest.raises(RuntimeError):
         jobs[0].result()
+
+
+COST = json.load(open(os.path.join(GOLDEN, "cost_plans.json")))
+
+
+@pytest.mark.parametrize("name", sorted(COST))
+def test_cost_based_planner_value(built, name):
+    """the sampled greedy planner end to end on the device: the reference's plan (same seed) and the reference's value"""
+    c = COST[name]
+    cwd, qasm, meas, _ = golden_paths(NETS[c["network"]])
+    out = qt.run_harness(["cost", qasm, meas, c["p"], c["seed"]], cwd=cwd, timeout=300)
+    assert "exception" not in out, out.get("exception")
+    val = complex(float(out["value"][0]), float(out["value"][1]))
+    assert _close(val, c["value"]), (val, c["value"])
+    assert out["plan"] == c["plan"] and int(out["flops"][0]) == c["flops"]

@@ -50,6 +50,30 @@ def test_stochastic_search_completes_and_is_seedable(built):
     assert a["plan"] != c["plan"]
 
 
+COST = json.load(open(os.path.join(GOLDEN, "cost_plans.json")))
+
+
+@pytest.mark.parametrize("name", sorted(COST))
+def test_cost_based_planner_draws_the_reference_plan(built, name):
+    """ContractionTools::Contract(CostContractSimple, p) is a randomised search; with the generator seeded like the
+    reference run that made the golden file it must take the same decisions draw by draw: identical plan and float ops"""
+    c = COST[name]
+    cwd, qasm, meas, _ = golden_paths(NETS[c["network"]])
+    out = qt.run_harness(["cost", qasm, meas, c["p"], c["seed"]], plan_only=True, cwd=cwd, timeout=120)
+    assert "exception" not in out, out.get("exception")
+    assert out["plan"] == c["plan"]
+    assert int(out["flops"][0]) == c["flops"] and int(out["nodes"][0]) == c["nodes"]
+
+
+def test_cost_based_planner_lookahead_two_terminates(built):
+    """pValue = 2: the reference redraws forever once a super-node has absorbed its whole neighbourhood
+    (ContractionTools.h:1002-1004); the mirror stops looking ahead there and still finishes with a complete plan"""
+    rec = NETS["qft8_X8"]
+    cwd, qasm, meas, _ = golden_paths(rec)
+    out = qt.run_harness(["cost", qasm, meas, 2, 1], plan_only=True, cwd=cwd, timeout=120)
+    assert "exception" not in out and int(out["nodes"][0]) == rec["nodes"] and len(out["plan"]) == len(rec["plan"])
+
+
 def test_bell_pair_worked_example(built):
     """the smallest plan KAT -- (0,2)->6, (3,5)->7, (7,4)->8, (6,8)->9, (1,9)->done; 356 units; 11 nodes"""
     rec = NETS["bell_00"]
