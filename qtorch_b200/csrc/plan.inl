@@ -418,16 +418,14 @@ int qtb_plan_run_slots(qtb_ctx *ctx, qtb_plan *pl, const int *slots, int n, doub
     }
     hostSum[0] = sr; hostSum[1] = si;
     // work actually done: the prefix once, the suffix n times
-    long long preUnits = 0; int preSteps = 0, preMicro = 0;
-    for (size_t si2 = 0; si2 < pre; si2++) {
-        const PlanSeg &sg = pl->segs[si2];
-        preSteps += sg.nSteps;
-        if (sg.micro) preMicro += sg.nSteps;
+    int preSteps = 0, preMicro = 0;
+    for (size_t k = 0; k < pre; k++) {
+        preSteps += pl->segs[k].nSteps;
+        if (pl->segs[k].micro) preMicro += pl->segs[k].nSteps;
     }
-    preUnits = pl->prefixUnits;
     ctx->stats.steps += preSteps + (long long)n * (pl->nSteps - preSteps);
     ctx->stats.micro_steps += preMicro + (long long)n * (pl->nMicroSteps - preMicro);
-    ctx->stats.units += preUnits + (long long)n * (pl->units - preUnits);
+    ctx->stats.units += pl->prefixUnits + (long long)n * (pl->units - pl->prefixUnits);
     ctx->stats.bytes_d2h += (long long)n * 16;
     return QTB_OK;
 }
@@ -478,11 +476,13 @@ int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const dou
             }
         CU(cudaEventRecord(ctx->forkEvent, ctx->stream));
         for (int a = 0; a < nAux; a++) CU(cudaStreamWaitEvent(ctx->auxStreams[a], ctx->forkEvent, 0));
-        for (int i = 0; i < n; i++) ST(plan_run_locked(ctx, plans[i], ctx->auxStreams[i % nAux]));
-        for (int a = 0; a < nAux; a++) {
+        int st = QTB_OK;
+        for (int i = 0; i < n && st == QTB_OK; i++) st = plan_run_locked(ctx, plans[i], ctx->auxStreams[i % nAux]);
+        for (int a = 0; a < nAux; a++) {              // always join: whatever was forked must be ordered before later main-stream work
             CU(cudaEventRecord(ctx->auxEvents[a], ctx->auxStreams[a]));
             CU(cudaStreamWaitEvent(ctx->stream, ctx->auxEvents[a], 0));
         }
+        ST(st);
     }
     // gather the n scalars: n tiny async copies into pinned memory, one wait
     if ((size_t)n > ctx->batchOutCap) {
