@@ -6,6 +6,10 @@
 //    scope here, so a small derivative-free Nelder-Mead ascent with an evaluation cap takes its place.  Same start
 //    point (beta = 0.392699, gamma = 0.785399, maxcut.cpp:155-157); the angle file is rewritten after every
 //    evaluation like the reference does (maxcut.cpp:199-202).
+//  * Multi-GPU: started once per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment (e.g.
+//    `torchrun --no-python --nproc-per-node N maxcutQAOA ...`), every process owns the edges e with e % WORLD_SIZE == RANK
+//    and the partial objectives meet in one NCCL allreduce per evaluation (device::Job::FromEnvironment).  All ranks
+//    run the same deterministic optimiser on the same reduced values; rank 0 alone writes files and reports.
 //  * Modes 1 and 2 add the final bit-string sampler (maxcut.cpp:29-140): the n-qubit circuit is planned once with the
 //    in-process min-fill ordering and the n conditional probabilities re-use one compiled device plan.
 #include <sys/stat.h>
@@ -90,16 +94,23 @@ int main(int argc, char *argv[]) {
         clock.start();
         ExtraData data(p, argv[1]);
         data.outputFile = outputPath;
-        QaoaObjective objective(data);
-        std::cout << "Planned " << data.pairs.size() << " edge terms in " << clock.getElapsed() << " seconds; " << objective.UnitsPerEvaluation()
-                  << " units and " << objective.LaunchesPerEvaluation() << " kernel launch(es) per objective evaluation" << std::endl;
+        const device::Job job = device::Job::FromEnvironment();
+        const bool lead = job.rank == 0;
+        QaoaObjective objective(data, job.rank, job.world, job.allreduce);
+        if (lead) {
+            std::cout << "Planned " << objective.OwnedEdges().size() << " of " << data.pairs.size() << " edge terms on rank 0 of " << job.world << " in "
+                      << clock.getElapsed() << " seconds; " << objective.UnitsPerEvaluation() << " units and " << objective.LaunchesPerEvaluation()
+                      << " kernel launch(es) per objective evaluation on this rank" << std::endl;
+        }
         std::vector<double> start(2 * p);
         for (int i = 0; i < p; ++i) { start[i] = 0.392699; start[i + p] = 0.785399; }
         double bestSeen = -1.0;
         auto F_p = [&](const std::vector<double> &bg) {
             const double v = objective(bg);
-            std::ofstream angles(outputPath);
-            for (double a : bg) angles << a << " ";
+            if (lead) {
+                std::ofstream angles(outputPath);
+                for (double a : bg) angles << a << " ";
+            }
             bestSeen = std::max(bestSeen, v);
             return v;
         };
@@ -108,14 +119,17 @@ int main(int argc, char *argv[]) {
         int evals = 0;
         const std::vector<double> best = nelderMeadMaximise(F_p, start, maxEvals, 0.1, evals);
         const double seconds = opt.getElapsed();
-        {
+        if (lead) {
             std::ofstream angles(outputPath);
             for (double a : best) angles << a << " ";
+            angles.close();
+            std::cout.precision(12);
+            std::cout << "F_p(start) evaluations: " << evals << ", best F_p = " << bestSeen << std::endl;
+            std::cout.precision(6);
+            std::cout << "Terms per second: " << evals * static_cast<double>(data.pairs.size()) / seconds << std::endl;
+            std::cout << "Took " << clock.getElapsed() << " seconds" << std::endl;
         }
-        std::cout << "F_p(start) evaluations: " << evals << ", best F_p = " << bestSeen << std::endl;
-        std::cout << "Terms per second: " << evals * static_cast<double>(data.pairs.size()) / seconds << std::endl;
-        std::cout << "Took " << clock.getElapsed() << " seconds" << std::endl;
-        if (mode == 2) {                      // angles, then the final string with them (maxcut.cpp:293-324)
+        if (mode == 2 && lead) {                      // angles, then the final string with them (maxcut.cpp:293-324)
             std::remove("tempAngles.txt");
             maxcutGetFinalString(argv[1], p, {}, best, argv[4]);
         }

@@ -10,10 +10,17 @@
 // planner logic can be tested and plans exported on machines without a GPU; it is NOT a CPU fallback --
 // tensors have no data in that mode and every value read returns NaN.
 #pragma once
+#include <unistd.h>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <functional>
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 #include "../../include/qtorch_b200.h"
 #include "Exceptions.h"
 
@@ -68,6 +75,56 @@ private:
     Engine() {}
     std::mutex mMu;
     qtb_ctx *mCtx{nullptr};
+};
+
+// One process per GPU, launched by any launcher that exports RANK / WORLD_SIZE / LOCAL_RANK (torchrun --no-python,
+// mpirun wrappers, a shell loop): joins the job's NCCL communicator and hands back the scalar allreduce the term
+// dispatcher needs (edges dealt round-robin, ONE ncclAllReduce of the partial objective per evaluation).
+// The NCCL unique id travels through a file: rank 0 writes it (atomically), the others wait for it.  Path:
+// QTORCH_NCCL_ID_FILE, else /tmp/qtorch_nccl_id.<MASTER_PORT or 0>.  Single-process runs (WORLD_SIZE unset or 1) skip
+// all of this and get an empty functor.
+struct Job {
+    int rank = 0, world = 1;
+    std::function<void(double *, int)> allreduce;      // in-place sum of n doubles over all ranks; empty when world == 1
+
+    static Job FromEnvironment() {
+        Job job;
+        if (const char *w = std::getenv("WORLD_SIZE")) job.world = std::max(1, std::atoi(w));
+        if (const char *r = std::getenv("RANK")) job.rank = std::atoi(r);
+        if (job.world == 1) { job.rank = 0; return job; }
+        if (job.rank < 0 || job.rank >= job.world) throw DeviceUnavailable("RANK outside [0, WORLD_SIZE)");
+        std::string path;
+        if (const char *f = std::getenv("QTORCH_NCCL_ID_FILE")) path = f;
+        else { const char *port = std::getenv("MASTER_PORT"); path = std::string("/tmp/qtorch_nccl_id.") + (port ? port : "0"); }
+        char id[QTB_UNIQUE_ID_BYTES];
+        if (job.rank == 0) {
+            check(qtb_comm_unique_id(id));
+            const std::string tmp = path + ".tmp." + std::to_string(static_cast<long>(getpid()));
+            { std::ofstream out(tmp, std::ios::binary); out.write(id, QTB_UNIQUE_ID_BYTES); }
+            if (std::rename(tmp.c_str(), path.c_str()) != 0) throw DeviceUnavailable("cannot publish the NCCL id at " + path);
+        } else {
+            bool got = false;
+            for (int tries = 0; tries < 1200 && !got; ++tries) {            // up to 60 s
+                std::ifstream in(path, std::ios::binary);
+                if (in && in.read(id, QTB_UNIQUE_ID_BYTES)) got = true;
+                else std::this_thread::sleep_for(std::chrono::milliseconds(50));
+            }
+            if (!got) throw DeviceUnavailable("no NCCL id from rank 0 at " + path);
+        }
+        qtb_ctx *ctx = Engine::Get().ctx();
+        check(qtb_comm_init(ctx, job.world, job.rank, id));
+        // everyone has joined once the first collective returns: rank 0 can take the id file away
+        std::vector<double> probe(2, 1.0);
+        check(qtb_allreduce_sum(ctx, probe.data(), 1));
+        if (job.rank == 0) std::remove(path.c_str());
+        job.allreduce = [ctx](double *v, int n) {
+            std::vector<double> buf(2 * static_cast<size_t>(n), 0.0);        // the C ABI reduces complex scalars
+            for (int i = 0; i < n; ++i) buf[2 * i] = v[i];
+            check(qtb_allreduce_sum(ctx, buf.data(), n));
+            for (int i = 0; i < n; ++i) v[i] = buf[2 * i];
+        };
+        return job;
+    }
 };
 
 }  // namespace device

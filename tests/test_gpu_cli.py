@@ -78,3 +78,34 @@ def test_maxcut_cli_improves_objective(built, tmp_path):
     assert best >= 32.259328920042 - 1e-9            # never worse than the reference's start point (golden F_p)
     angles = [float(x) for x in open(os.path.join(work, "angles.txt")).read().split()]
     assert len(angles) == 2
+
+
+def test_maxcut_cli_two_ranks_reach_the_single_rank_optimum(built, tmp_path):
+    """maxcutQAOA started once per GPU (RANK / WORLD_SIZE / LOCAL_RANK, NCCL id through a file): edges dealt over the
+    ranks, one allreduce per evaluation -- same optimiser trajectory, so the same best F_p as one process finds"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (NCCL refuses two ranks on one device)")
+    exe = os.path.join(ROOT, "qtorch_b200", "bin", "maxcutQAOA")
+    graph = os.path.join(GOLDEN, "Samples", "3regRand30Node50.dgf")
+
+    def best_of(stdout):
+        return float([l for l in stdout.splitlines() if "best F_p" in l][0].split("=")[-1])
+
+    solo = os.path.join(str(tmp_path), "solo")
+    os.makedirs(solo)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["QTORCH_QUIET"] = "1"
+    r = subprocess.run([exe, graph, "1", "0", "angles.txt", "40"], cwd=solo, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-1000:]
+    duo = os.path.join(str(tmp_path), "duo")
+    os.makedirs(duo)
+    idfile = os.path.join(duo, "nccl.id")
+    procs = [subprocess.Popen([exe, graph, "1", "0", "angles.txt", "40"], cwd=duo, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              env=dict(env, RANK=str(k), WORLD_SIZE="2", LOCAL_RANK=str(k), QTORCH_NCCL_ID_FILE=idfile)) for k in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "rank 0 of 2" in outs[0] and "best F_p" not in outs[1]          # rank 0 alone reports
+    assert abs(best_of(outs[0]) - best_of(r.stdout)) <= 1e-9
+    assert open(os.path.join(duo, "angles.txt")).read().split() == open(os.path.join(solo, "angles.txt")).read().split()
+    assert not os.path.exists(idfile)
