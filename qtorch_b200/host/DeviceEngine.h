@@ -10,8 +10,10 @@
 // planner logic can be tested and plans exported on machines without a GPU; it is NOT a CPU fallback --
 // tensors have no data in that mode and every value read returns NaN.
 #pragma once
+#include <sys/stat.h>
 #include <unistd.h>
 #include <chrono>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -103,10 +105,14 @@ struct Job {
             { std::ofstream out(tmp, std::ios::binary); out.write(id, QTB_UNIQUE_ID_BYTES); }
             if (std::rename(tmp.c_str(), path.c_str()) != 0) throw DeviceUnavailable("cannot publish the NCCL id at " + path);
         } else {
+            // a file left behind by a job that died is older than this process: only an id published within the last
+            // 30 s before this rank started (launchers start ranks together) or later is accepted
+            const time_t notBefore = time(nullptr) - 30;
             bool got = false;
             for (int tries = 0; tries < 1200 && !got; ++tries) {            // up to 60 s
+                struct stat st;
                 std::ifstream in(path, std::ios::binary);
-                if (in && in.read(id, QTB_UNIQUE_ID_BYTES)) got = true;
+                if (stat(path.c_str(), &st) == 0 && st.st_mtime >= notBefore && in && in.read(id, QTB_UNIQUE_ID_BYTES)) got = true;
                 else std::this_thread::sleep_for(std::chrono::milliseconds(50));
             }
             if (!got) throw DeviceUnavailable("no NCCL id from rank 0 at " + path);
