@@ -165,7 +165,8 @@ int qtb_ctx_reset_stats(qtb_ctx *ctx);
 typedef struct qtb_step_trace {
     int32_t rank_a, rank_b, k, kernel;   /* kernel: 0 grouped micro-steps (k = number of steps in the group), 1 thread-per-output,
                                             2 DMMA tile kernel (k_gett), 3 warp-per-output, 5 split-K / inner product,
-                                            6 DMMA tile kernel fused with the inner product that follows it               */
+                                            6 DMMA tile kernel fused with the inner product that follows it,
+                                            7 streaming kernel (big tensor x tensor of <= 64 elements)                    */
     float ms;
 } qtb_step_trace;
 /* Largest step (4^n complex multiply-adds, n = 0..8) that may ride in a grouped micro-step launch.  A micro-step runs

@@ -1,0 +1,73 @@
+// qtorch_b200/csrc/apply.cuh -- streaming steps: a big Node tensor contracted with a tiny one (<= 64 elements).
+//
+// The "gate / measurement cap applied to a large intermediate" shape of Network::ContractIndices
+// (/root/reference/src/Network.h:892-935 with rB <= 3): arithmetic intensity <= 2 flop/B, so the step is a pure
+// HBM stream -- read the big operand once, write the result once.  One thread per free index x of the big operand:
+//      C[x, y] = sum_s X[ins(x) + kOff[s]] * W[s][y]            K = 4^k <= 16 loads of 16 B, N = 4^nfy <= 16 outputs
+// ins(x) opens the (at most two) 2-bit holes of the shared legs in x, W (the small operand re-ordered as [s][y]) sits in
+// shared memory and is read as a broadcast.  Consecutive threads read consecutive elements of X for every s and write
+// consecutive elements of C for every y; when the small operand's legs come first in C (C index = y + N x) the block's
+// 256 N outputs form one contiguous run and are transposed through shared memory so that the stores stream as well.
+// No tile staging, no tensor pipe (the DMMA tile kernel pads N to 8 and idles on these).  N <= 4, K <= 16.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qtb {
+
+struct ApplyParams {
+    const double2 *X;             // big operand, original layout
+    const double2 *Y;             // small operand (<= 64 elements)
+    double2 *C;
+    uint64_t M;                   // free elements of X = number of threads
+    uint8_t nHoles;               // = k (0, 1 or 2)
+    uint8_t holeBit[2];           // bit position of each shared leg inside X's element index, ascending
+    uint8_t yFirst;               // 1: C index = y + N * x (small operand is the reference's node A), 0: x + M * y
+    uint32_t kOff[16];            // element offset inside X of summed value s
+    uint8_t yIdx[16][4];          // element index inside Y of (s, y)
+};
+
+template <int K, int N>
+__global__ void __launch_bounds__(256) k_apply(const ApplyParams p) {
+    __shared__ double2 W[K * N];
+    __shared__ double2 T[N > 1 ? 256 * (N + 1) : 1];      // yFirst: [x in block][y], row stride N + 1 (conflict-free STS.128)
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) W[i] = p.Y[p.yIdx[i / N][i % N]];
+    __syncthreads();
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;        // M is a multiple of the block size
+    uint64_t off = x;
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+        if (j < p.nHoles) { const int h = p.holeBit[j]; off = ((off >> h) << (h + 2)) | (off & ((1ull << h) - 1)); }
+    double2 xv[K];
+#pragma unroll
+    for (int s = 0; s < K; s++) xv[s] = __ldcs(p.X + off + p.kOff[s]);        // streamed once: evict-first
+    double accR[N], accI[N];
+#pragma unroll
+    for (int y = 0; y < N; y++) accR[y] = accI[y] = 0.0;
+#pragma unroll
+    for (int s = 0; s < K; s++)
+#pragma unroll
+        for (int y = 0; y < N; y++) {
+            const double2 w = W[s * N + y];
+            accR[y] = fma(xv[s].x, w.x, accR[y]);
+            accR[y] = fma(-xv[s].y, w.y, accR[y]);
+            accI[y] = fma(xv[s].x, w.y, accI[y]);
+            accI[y] = fma(xv[s].y, w.x, accI[y]);
+        }
+    if (N > 1 && p.yFirst) {
+#pragma unroll
+        for (int y = 0; y < N; y++) T[threadIdx.x * (N + 1) + y] = make_double2(accR[y], accI[y]);
+        __syncthreads();
+        double2 *c = p.C + (uint64_t)blockIdx.x * blockDim.x * N;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const int e = j * 256 + threadIdx.x;
+            __stcs(c + e, T[(e / N) * (N + 1) + (e % N)]);
+        }
+    } else {
+#pragma unroll
+        for (int y = 0; y < N; y++) __stcs(p.C + x + p.M * y, make_double2(accR[y], accI[y]));
+    }
+}
+
+}  // namespace qtb

@@ -9,7 +9,7 @@
 #define QTB_MAXR 16
 
 // kernel families (DevStep::kind, qtb_step_trace::kernel)
-enum StepKind { KIND_MICRO = 0, KIND_THREAD = 1, KIND_GETT = 2, KIND_WARP = 3, KIND_COPY = 4, KIND_REDUCE = 5, KIND_FUSED = 6 };
+enum StepKind { KIND_MICRO = 0, KIND_THREAD = 1, KIND_GETT = 2, KIND_WARP = 3, KIND_COPY = 4, KIND_REDUCE = 5, KIND_FUSED = 6, KIND_APPLY = 7 };
 
 struct DevStep {
     const double2 *A;

@@ -293,3 +293,42 @@ def test_fused_dmma_step_plus_inner_product(engine, t_is_a, shape):
     got = plan.run_host([A, B, D])[0]
     assert plan.launches == 2 and abs(got - ref[0]) <= 1e-11 * max(1.0, abs(ref[0]))
     plan.destroy()
+
+
+@pytest.mark.parametrize("rA,rB,pA,pB", [
+    (9, 1, [0], [0]),                   # measurement cap on leg 0: K=4, N=1, hole at the bottom
+    (9, 1, [8], [0]),                   # ... on the top leg
+    (9, 1, [4], [0]),                   # ... in the middle
+    (1, 9, [0], [5]),                   # roles exchanged (the cap is the reference's node A)
+    (9, 2, [3], [1]),                   # 1-qubit gate: K=4, N=4
+    (2, 9, [0], [7]),                   # same, gate first: C = y + 4 x
+    (9, 2, [0, 1], [1, 0]),             # K=16, N=1, both holes at the bottom: stays with the tile kernel
+    (9, 2, [0, 5], [1, 0]),             # K=16, N=1: pairs crossed
+    (9, 2, [2, 7], [0, 1]),             # K=16, N=1
+    (9, 3, [0, 8], [2, 0]),             # K=16, N=4
+    (3, 9, [0, 2], [8, 3]),             # K=16, N=4, small operand first, its shared legs out of order in the big one
+    (8, 1, [], []),                     # outer product with a rank-1 tensor: K=1, N=4
+    (1, 8, [], []),                     # outer product, small first: C = y + 4 x
+    (10, 0, [], []),                    # scaling by a scalar tensor: K=1, N=1
+])
+def test_streaming_apply_steps(engine, rA, rB, pA, pB):
+    """big tensor x tiny tensor (<= 64 elements): the one-thread-per-free-index streaming kernel (apply.cuh)"""
+    engine.trace(True)
+    engine.read_trace()
+    _check(engine, rA, rB, pA, pB, seed=61)
+    kinds = [t["kernel"] for t in engine.read_trace() if t["kernel"] != 0]       # (uploads ride in a grouped launch: code 0)
+    engine.trace(False)
+    if os.environ.get("QTB_NO_APPLY") != "1":
+        assert kinds == [2 if (pA, pB) == ([0, 1], [1, 0]) else 7], kinds
+
+
+def test_tile_kernels_without_the_streaming_class():
+    """QTB_NO_APPLY=1 sends the gate-application shapes back through the DMMA tile kernel (k_gett 256x16 / 256x8 tiles,
+    TK = 4): those instantiations must stay correct.  The switch is read once per process, hence the child."""
+    import subprocess
+    import sys
+    env = dict(os.environ, QTB_NO_APPLY="1", QTORCH_QUIET="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "gett_steps or random_leg_maps or streaming_apply_steps"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:]
