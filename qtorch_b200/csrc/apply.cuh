@@ -70,4 +70,45 @@ __global__ void __launch_bounds__(256) k_apply(const ApplyParams p) {
     }
 }
 
+// Both shared legs are the big operand's two lowest legs: the 16 summands of an output are ONE 256-byte run.  Four lanes
+// share an output -- lane q reads the 64-byte quarter q of the run (so a warp's requests tile 2 KB without gaps), sums
+// its four terms, and two shuffle steps add the quarters.  yIdx / W are indexed by MEMORY offset m = 4 q + i here.
+template <int N>
+__global__ void __launch_bounds__(256) k_apply_lowpair(const ApplyParams p) {
+    // W[q][i][y] with one element of padding per quarter: the four quarters a warp reads side by side sit in different banks
+    constexpr int QS = 4 * N + 1;
+    __shared__ double2 W[4 * QS];
+    for (int i = threadIdx.x; i < 16 * N; i += blockDim.x) W[(i / (4 * N)) * QS + i % (4 * N)] = p.Y[p.yIdx[i / N][i % N]];
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // 4 M threads, a multiple of the block size
+    const uint64_t x = t >> 2;
+    const int q = (int)(t & 3);
+    const double2 *src = p.X + (x << 4) + 4 * q;
+    double2 xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) xv[i] = __ldcs(src + i);
+    double accR[N], accI[N];
+#pragma unroll
+    for (int y = 0; y < N; y++) accR[y] = accI[y] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int y = 0; y < N; y++) {
+            const double2 w = W[q * QS + i * N + y];
+            accR[y] = fma(xv[i].x, w.x, accR[y]);
+            accR[y] = fma(-xv[i].y, w.y, accR[y]);
+            accI[y] = fma(xv[i].x, w.y, accI[y]);
+            accI[y] = fma(xv[i].y, w.x, accI[y]);
+        }
+#pragma unroll
+    for (int y = 0; y < N; y++) {
+        accR[y] += __shfl_xor_sync(0xffffffffu, accR[y], 1); accI[y] += __shfl_xor_sync(0xffffffffu, accI[y], 1);
+        accR[y] += __shfl_xor_sync(0xffffffffu, accR[y], 2); accI[y] += __shfl_xor_sync(0xffffffffu, accI[y], 2);
+    }
+    if (q == 0) {
+#pragma unroll
+        for (int y = 0; y < N; y++) __stcs(p.yFirst ? p.C + x * N + y : p.C + x + p.M * y, make_double2(accR[y], accI[y]));
+    }
+}
+
 }  // namespace qtb

@@ -141,13 +141,13 @@ static int choose_kind(const StepGeom &g, GettChoice &gc, int microLog4) {
     const int bigFree = std::max(g.nfa, g.nfb), smallFree = std::min(g.nfa, g.nfb);
     if (!force_generic() && g.rC <= 2 && g.k >= 6) return KIND_REDUCE;       // long sums, <= 16 outputs: split-K
     // big tensor x tiny tensor (<= 64 elements, <= 4 outputs per free index): a pure stream, one thread per free index.
-    // Not when both shared legs are the big operand's two lowest legs: a thread's 16 loads are then one 256-byte run and
-    // the warp's requests stride by 256 B -- the tile kernel's staged gather is faster there (0.94 vs 1.02 ms at rank 14).
+    // One exception stays with the tile kernel (0.87 vs 1.46 ms at rank 14): both shared legs are the big operand's two
+    // lowest legs AND there are four outputs per free index.
     if (!force_generic() && apply_enabled() && bigFree >= 4 && g.k <= 2 && smallFree <= 1) {
         const bool sw = g.nfb > g.nfa;
         const int *posX = sw ? g.posB : g.posA;
         const bool lowPair = g.k == 2 && std::min(posX[0], posX[1]) == 0 && std::max(posX[0], posX[1]) == 1;
-        if (!lowPair) { gc.swap = sw; return KIND_APPLY; }
+        if (!(lowPair && smallFree == 1)) { gc.swap = sw; return KIND_APPLY; }
     }
     if (!force_generic() && bigFree >= 4 && g.k >= 1) {
         gc.swap = g.nfb > g.nfa;
@@ -432,6 +432,18 @@ static int launch_apply(qtb_ctx *ctx, const StepGeom &g, bool swap, const double
             for (int i = 0; i < nfy; i++) o += ((y >> (2 * i)) & 3) << (2 * freeY[i]);
             p.yIdx[sv][y] = (uint8_t)o;
         }
+    }
+    // both shared legs are X's two lowest legs: four lanes per output, each reading a 64-byte quarter of the 256-byte run
+    if (g.k == 2 && std::min(posX[0], posX[1]) == 0 && std::max(posX[0], posX[1]) == 1) {
+        uint8_t byMem[16][4];
+        for (int sv = 0; sv < K; sv++) memcpy(byMem[p.kOff[sv]], p.yIdx[sv], 4);      // kOff is a permutation of 0..15 here
+        memcpy(p.yIdx, byMem, sizeof(byMem));
+        const unsigned grid4 = (unsigned)(p.M * 4 / 256);
+        if (nfy != 0) return fail(QTB_ERR_INVALID, "step outside the streaming class");
+        k_apply_lowpair<1><<<grid4, 256, 0, s>>>(p);
+        CU(cudaGetLastError());
+        ctx->stats.launches++;
+        return QTB_OK;
     }
     const unsigned grid = (unsigned)(p.M / 256);
     switch (g.k * 4 + nfy) {

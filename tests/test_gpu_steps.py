@@ -302,7 +302,9 @@ def test_fused_dmma_step_plus_inner_product(engine, t_is_a, shape):
     (1, 9, [0], [5]),                   # roles exchanged (the cap is the reference's node A)
     (9, 2, [3], [1]),                   # 1-qubit gate: K=4, N=4
     (2, 9, [0], [7]),                   # same, gate first: C = y + 4 x
-    (9, 2, [0, 1], [1, 0]),             # K=16, N=1, both holes at the bottom: stays with the tile kernel
+    (9, 2, [0, 1], [1, 0]),             # K=16, N=1, both holes at the bottom (four lanes per output), pairs crossed
+    (9, 3, [0, 1], [0, 2]),             # ... with N=4: stays with the tile kernel
+    (3, 9, [1, 2], [1, 0]),             # ... N=4, small operand first: tile kernel
     (9, 2, [0, 5], [1, 0]),             # K=16, N=1: pairs crossed
     (9, 2, [2, 7], [0, 1]),             # K=16, N=1
     (9, 3, [0, 8], [2, 0]),             # K=16, N=4
@@ -319,7 +321,7 @@ def test_streaming_apply_steps(engine, rA, rB, pA, pB):
     kinds = [t["kernel"] for t in engine.read_trace() if t["kernel"] != 0]       # (uploads ride in a grouped launch: code 0)
     engine.trace(False)
     if os.environ.get("QTB_NO_APPLY") != "1":
-        assert kinds == [2 if (pA, pB) == ([0, 1], [1, 0]) else 7], kinds
+        assert kinds == [2 if (len(pA) == 2 and min(rA, rB) == 3 and sorted(pA if rA > rB else pB) == [0, 1]) else 7], kinds
 
 
 def test_tile_kernels_without_the_streaming_class():
