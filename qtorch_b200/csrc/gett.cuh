@@ -63,6 +63,10 @@ __device__ __forceinline__ double dneg(const double v) {
 __device__ __forceinline__ void cp_async16(uint32_t smemAddr, const void *g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr), "l"(g) : "memory");
 }
+// one 32-byte sector per store (sm_100 STG.256): two adjacent complex results of a lane
+__device__ __forceinline__ void st_global_256(double2 *dst, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -430,6 +434,12 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
             const uint32_t tile = blockIdx.x + ti * gridDim.x;
             const uint32_t ty = tile / p.nTilesX, tx = tile - ty * p.nTilesX;
             double2 *cb = p.C + hitab_lookup(hi[4], tx, xParts) + hitab_lookup(hi[5], ty, yParts);
+            // D = C^T (the y legs come first in C): a lane's two results y0, y0 + 1 are neighbours in memory and fill one
+            // 32-byte sector -- written with one 256-bit store instead of two half-sector stores (streaming tile shapes
+            // only: there the store stream is the bound, 1.23 -> 0.94 ms for (3,13,k=1); the compute-bound 64x64 / 128x64
+            // configurations keep the plain epilogue, whose schedule the extra path disturbed: 3.52 -> 3.68 ms)
+            constexpr bool PAIRABLE = (WY == 1);
+            const bool pairStore = PAIRABLE && nyValid >= 2 && p.shCy[0] == 0;
 #pragma unroll
             for (int i = 0; i < FX; i++) {
                 const uint32_t ox = tCx[wx0 + i * 8 + g];
@@ -443,8 +453,12 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
                     } else {
                         re0 = accR[i][j][0]; im0 = accI[i][j][0]; re1 = accR[i][j][1]; im1 = accI[i][j][1];
                     }
-                    if ((uint32_t)y0 < nyValid) cb[ox + tCy[y0]] = make_double2(re0, im0);
-                    if ((uint32_t)(y0 + 1) < nyValid) cb[ox + tCy[y0 + 1]] = make_double2(re1, im1);
+                    if (PAIRABLE && pairStore) {
+                        if ((uint32_t)y0 < nyValid) st_global_256(cb + ox + tCy[y0], re0, im0, re1, im1);
+                    } else {
+                        if ((uint32_t)y0 < nyValid) cb[ox + tCy[y0]] = make_double2(re0, im0);
+                        if ((uint32_t)(y0 + 1) < nyValid) cb[ox + tCy[y0 + 1]] = make_double2(re1, im1);
+                    }
                 }
             }
         }
