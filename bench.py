@@ -347,9 +347,12 @@ def main():
                     "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
                     # achieved counts the ALGORITHMIC 8 flops per complex MAC; the 3M kernel issues 6 on the tensor pipe
                     "tensor_pipe_flops_per_unit": 6 if three_m else 8, "tensor_pipe_frac": ach * (0.75 if three_m else 1.0) / FP64_PEAK_TFLOPS,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_summary.txt); algorithmic 4.33e9
-                    "traffic": 4.42e9, "launches_timed": len(gett), "avg_ms": avg_ms,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one (10,10,k=3 -> 14) launch, ncu --set full
+                    # (profiles/r01_ncu_summary.txt: 0.259 GB read + 4.238 GB written); algorithmic 16 * (2 * 4^10 + 4^14) = 4.33e9
+                    "traffic": 4.50e9, "launches_timed": len(gett), "avg_ms": avg_ms,
                     "share_of_step": sum(r["ms"] for r in gett) / total_ms,
+                    # the fourth rank-14 step runs fused with the closing inner product (trace code 6, same tile kernel)
+                    "fused_step_share_of_step": sum(r["ms"] for r in trace if r["kernel"] == 6) / total_ms,
                     "peak_source": "measured: tools/probe_fp64 DMMA m8n8k4 on this pool's B200 (profiles/r01_probe_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry"}
         by_kind = {}
         for r in trace:
