@@ -1,9 +1,8 @@
 #!/bin/bash
+# tools/gpu_try.sh -- scratch: a quick GPU check between full rounds (subset of the parity tests + a short bench)
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-for shape in "10 10 3 7 8 9 0 1 2" "6 14 3 1 3 5 0 6 12" "9 11 3 0 4 8 2 5 9" "10 10 3 7 8 9 0 1 2"; do
-timeout 120 python tools/prof_step.py $shape 5 2>&1 | tail -3 | tee -a gpurun_out/try.log
-done
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "not drop_in" 2>&1 | tail -5 | tee gpurun_out/try.log
 timeout 600 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_try.log
 python - <<PY
 import json
