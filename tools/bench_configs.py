@@ -54,7 +54,29 @@ def time_maxcut(name, evals=200):
     q.close()
 
 
+def time_plan_replay(name, reps=50):
+    """the same network as a compiled plan replayed on resident inputs (one CUDA graph / grouped launches): device time only"""
+    rec = NETS[name]
+    qasm, meas, ordering = (os.path.join(G, rec[k]) for k in ("qasm", "measure", "ordering"))
+    ranks, steps, inputs, flops = host_api.export_plan_linegraph(qasm, meas, ordering, bool(rec["reduce"]))
+    plan = eng.plan(ranks, steps)
+    plan.upload_inputs(inputs)
+    for _ in range(3):
+        plan.run_device()
+    val = complex(plan.read_output()[0])
+    eng.timer_start()
+    for _ in range(reps):
+        plan.run_device()
+    ms = eng.timer_stop() / reps
+    ok = abs(val - complex(*rec["value"])) <= 1e-10 * max(1.0, abs(complex(*rec["value"])))
+    print(json.dumps({"config": name + " (compiled plan replay)", "matches_reference": bool(ok), "steps": len(steps), "launches": plan.launches,
+                      "ms_per_replay": ms, "steps_per_s": len(steps) / (ms * 1e-3), "units": flops}))
+    plan.destroy()
+
+
 time_network("qft8_X8")
+time_plan_replay("qft8_X8")
+time_plan_replay("ghz1000_zeros")
 time_network("ghz1000_zeros")
 time_network("ghz1000_ones")
 time_network("qaoa20_node5_m125")
