@@ -1,8 +1,8 @@
 #!/bin/bash
+# tools/gpu_try.sh -- scratch: a quick GPU check between full rounds (parity tests without the 90 s drop-in suite + a short bench)
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "fused or config2 or qaoa30 or slic" 2>&1 | tail -4 | tee gpurun_out/try.log
-timeout 200 python tools/prof_fused.py 3 2>&1 | tail -3 | tee -a gpurun_out/try.log
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 -k "not drop_in" 2>&1 | tail -5 | tee gpurun_out/try.log
 timeout 600 python bench.py --steps 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_try.log
 python - <<PY
 import json
