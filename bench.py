@@ -248,14 +248,18 @@ def main():
     stats_e2e = eng.stats()
 
     # ---------------- second half of the metric: one amplitude index-sliced over the ranks --------------------------
-    # The <Z27 Z29> term cut into 4^2 = 16 slices (qtorch_b200/slicing.py: two wires chosen greedily, peak rank 14 -> 12,
+    # The <Z27 Z29> term cut into 4^s slices (qtorch_b200/slicing.py: wires chosen greedily; two wires: peak rank 14 -> 12,
     # total units x1.005); slices dealt round-robin to ranks, one compiled plan, per-slice inputs staged in HBM, the
     # partial sums meet in one NCCL allreduce per amplitude.  Strong scaling of ONE expectation value.
     from qtorch_b200 import slicing
     from qtorch_b200.dispatch import Dispatcher
     golden_rec = json.load(open(NETS))["qaoa30_z27z29"]
     g_ranks, g_steps, g_inputs, _ = host_api.export_plan_linegraph(QASM, os.path.join(GOLDEN, golden_rec["measure"]), ORDERING, True)
-    SLICE_WIRES = 2
+    # as few slices as give every rank work: 4 slices (one wire, peak rank 13) up to 4 ranks, 16 slices (two wires, peak
+    # rank 12) for 8 -- bigger slices keep the tile kernel's prologue and tail a smaller share of each step
+    SLICE_WIRES = 1
+    while 4 ** SLICE_WIRES < world:
+        SLICE_WIRES += 1
     wires = slicing.choose_wires(g_ranks, g_steps, SLICE_WIRES)
     all_sl = slicing.all_slices(wires)
     plan_launches = plan.launches
