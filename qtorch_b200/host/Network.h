@@ -80,7 +80,10 @@ public:
     const std::vector<std::shared_ptr<Node>> &GetAllNodes() const noexcept { return mAllNodes; }
     void SetNumThreads(const int numThreads) noexcept { mNumberOfThreads = numThreads; }   // kept for API parity: the GPU ignores it
     const int GetNumQubits() const noexcept { return mNumberOfQubits; }
-    const std::vector<std::shared_ptr<Node>> &GetUncontractedNodes() const noexcept { return mUncontractedNodes; }
+    const std::vector<std::shared_ptr<Node>> &GetUncontractedNodes() const noexcept {
+        const_cast<Network *>(this)->CompactLive();
+        return mUncontractedNodes;
+    }
     const bool IsDone() noexcept { return mDone; }
     void MoveInitialStatesToBack();
     void ReduceCircuit();
@@ -117,7 +120,40 @@ private:
     bool mFailure{false};
     std::vector<std::shared_ptr<Node>> mAllNodes;
     std::vector<std::vector<std::shared_ptr<Node>>> mNodesByWire;
+    // The reference erases operand A from this vector and puts C into B's slot on every step (Network.h:860-861), an
+    // O(#nodes) shift per step.  Here the erase leaves a hole (nullptr) and the holes are squeezed out, order preserved,
+    // the next time anybody LOOKS at the list (GetUncontractedNodes and the internal readers): planners that inspect
+    // the list between steps see exactly the reference's vector, LGContract's 3000-step GHZ walk never pays the shifts.
     std::vector<std::shared_ptr<Node>> mUncontractedNodes;
+    size_t mLiveHoles{0};
+    size_t LiveCount() const noexcept { return mUncontractedNodes.size() - mLiveHoles; }
+    void ReindexLive() noexcept {
+        for (size_t i = 0; i < mUncontractedNodes.size(); ++i)
+            if (mUncontractedNodes[i]) mUncontractedNodes[i]->mLiveSlot = static_cast<int>(i);
+    }
+    void CompactLive() noexcept {
+        if (mLiveHoles == 0) return;
+        size_t keep = 0;
+        for (size_t i = 0; i < mUncontractedNodes.size(); ++i)
+            if (mUncontractedNodes[i]) { if (keep != i) mUncontractedNodes[keep] = std::move(mUncontractedNodes[i]); ++keep; }
+        mUncontractedNodes.resize(keep);
+        mLiveHoles = 0;
+        ReindexLive();
+    }
+    // operand A leaves the list, the result C takes operand B's place
+    void RetireOperands(const std::shared_ptr<Node> &nodeA, const std::shared_ptr<Node> &nodeB, const std::shared_ptr<Node> &nodeC) {
+        auto slotOf = [this](const std::shared_ptr<Node> &n) -> int {
+            const int s = n->mLiveSlot;
+            if (s >= 0 && s < static_cast<int>(mUncontractedNodes.size()) && mUncontractedNodes[s] == n) return s;
+            CompactLive();                                   // not indexed (list edited from outside): search like the reference
+            auto it = std::find(mUncontractedNodes.begin(), mUncontractedNodes.end(), n);
+            return it == mUncontractedNodes.end() ? -1 : static_cast<int>(it - mUncontractedNodes.begin());
+        };
+        const int a = slotOf(nodeA);
+        if (a >= 0) { mUncontractedNodes[a].reset(); ++mLiveHoles; nodeA->mLiveSlot = -1; }
+        const int b = slotOf(nodeB);
+        if (b >= 0) { mUncontractedNodes[b] = nodeC; nodeC->mLiveSlot = b; nodeB->mLiveSlot = -1; }
+    }
     std::unordered_map<std::string, std::string> mArbitraryOneQubitGates, mArbitraryTwoQubitGates;
     long long mNumFloatOps{0};
     int mNumberOfThreads{8};
@@ -164,6 +200,7 @@ inline void Network::Reset() {
     mAllNodes.clear();
     mNodesByWire.clear();
     mUncontractedNodes.clear();
+    mLiveHoles = 0;
     mArbitraryOneQubitGates.clear();
     mArbitraryTwoQubitGates.clear();
     mPlan.clear();
@@ -245,6 +282,8 @@ inline void Network::ParseStreams(std::istream &input, std::istream &measureStre
     mNetworkParsingNodes.clear();
     mNetworkParsingWires.clear();
     mUncontractedNodes = mAllNodes;
+    mLiveHoles = 0;
+    ReindexLive();
     mNumOriginalNodes = static_cast<int>(mAllNodes.size());
 }
 
@@ -436,8 +475,7 @@ inline std::shared_ptr<Node> Network::ContractNodes(std::shared_ptr<Node> nodeA,
         rec.c = marker->mID;
         mPlan.push_back(rec);
         mAllNodes.push_back(marker);
-        FindAndRemove(mUncontractedNodes, nodeA);
-        FindAndReplace(mUncontractedNodes, nodeB, nodeC);
+        RetireOperands(nodeA, nodeB, nodeC);
         nodeA->ClearNodeData();
         nodeB->ClearNodeData();
         return nullptr;
@@ -450,8 +488,7 @@ inline std::shared_ptr<Node> Network::ContractNodes(std::shared_ptr<Node> nodeA,
     mAllNodes.push_back(nodeC);
     nodeA->ClearNodeData();           // stream-ordered free: the step that reads them is already enqueued
     nodeB->ClearNodeData();
-    FindAndRemove(mUncontractedNodes, nodeA);
-    FindAndReplace(mUncontractedNodes, nodeB, nodeC);     // C inherits B's slot
+    RetireOperands(nodeA, nodeB, nodeC);                  // C inherits B's slot
     return nodeC;
 }
 
@@ -487,7 +524,7 @@ inline void Network::ContractIndices(const std::vector<std::pair<bool, int>> &to
         if ((std::abs(mFinalVal.real()) <= 1.0e-30 && std::abs(mFinalVal.imag()) <= 1.0e-30) ||
             (nodeA->mRank == 0 && nodeB->mRank == 0))
             mFinalSource = nodeC;                      // read back lazily: no sync inside the contraction
-        if (mUncontractedNodes.size() == 2) mDone = true;
+        if (LiveCount() == 2) mDone = true;
     }
 }
 
@@ -520,6 +557,7 @@ inline void Network::ResolveFinalValue() {
 
 inline void Network::ContractNetworkLinearly() {
     while (!mDone) {
+        CompactLive();
         const std::shared_ptr<Wire> &w = mUncontractedNodes[0]->GetWires()[0];
         if (w->GetNodeA().expired() || w->GetNodeB().expired()) throw InvalidContractionMethod();
         ContractNodes(w->GetNodeA().lock(), w->GetNodeB().lock(), 1000);
@@ -534,7 +572,9 @@ inline void Network::MoveInitialStatesToBack() {
         for (long i = last; i >= first && i >= 0; --i) std::swap(v[count++], v[static_cast<size_t>(i)]);
     };
     rotate(mAllNodes);
+    CompactLive();
     rotate(mUncontractedNodes);
+    ReindexLive();
 }
 
 // =====================================================================================================
@@ -575,17 +615,26 @@ inline void Network::ReduceCircuit() {
     std::vector<std::vector<std::shared_ptr<Node>>> merged(nq);
     std::vector<std::shared_ptr<Node>> head(nq);      // last node placed on each line
     std::vector<int> cursor(nq, 0);
-    std::vector<bool> advanced(nq, false);
+    std::vector<char> advanced(nq, 0);
     bool fusedThisSweep = false;
-    std::vector<int> active(nq);                        // lines that still have nodes to place, ascending
-    for (int q = 0; q < nq; ++q) active[q] = q;
-    for (;;) {
-        for (int q : active) {
-            if (cursor[q] >= static_cast<int>(mNodesByWire[q].size()) || advanced[q]) continue;
+    // The reference sweeps over every line again and again, each line advancing by at most one node per sweep
+    // (Network.h:1050-1112).  A line that could not advance stays blocked until the line it waits for moves, so a sweep
+    // only has to visit (in ascending order, like the reference) the lines that advanced in the previous sweep and the
+    // lines of the nodes those now have in front of them: same decisions in the same order, O(#nodes log) instead of
+    // O(depth x qubits) -- the 1000-qubit GHZ chain has depth 1000.
+    std::vector<int> visit(nq), movedLines, next;
+    std::vector<char> queued(nq, 0);
+    for (int q = 0; q < nq; ++q) visit[q] = q;
+    auto pending = [&](int q) { return cursor[q] < static_cast<int>(mNodesByWire[q].size()); };
+    while (!visit.empty()) {
+        movedLines.clear();
+        for (int q : visit) {
+            if (!pending(q) || advanced[q]) continue;
             Node *peek = mNodesByWire[q][cursor[q]].get();       // no shared_ptr copy in this (hot) scan
             if (peek->mRank == 1) {
                 head[q] = mNodesByWire[q][cursor[q]];
-                advanced[q] = true;
+                advanced[q] = 1;
+                movedLines.push_back(q);
                 ++cursor[q];
                 continue;
             }
@@ -606,26 +655,33 @@ inline void Network::ReduceCircuit() {
                 head[qb] = cand;
             }
             ++cursor[qa]; ++cursor[qb];
-            advanced[qa] = advanced[qb] = true;
+            advanced[qa] = advanced[qb] = 1;
+            movedLines.push_back(qa);
+            movedLines.push_back(qb);
         }
-        bool any = false;
-        for (int q : active) {
-            if (advanced[q]) {
-                any = true;
-                if (fusedThisSweep && !merged[q].empty()) merged[q].back() = head[q];
-                else merged[q].push_back(head[q]);
-                advanced[q] = false;
-            }
-            // The reference pads waiting lines with a nullptr per sweep (Network.h:1102-1104).  Every reader of
-            // mNodesByWire skips nullptr entries (Network.h:1179,1217), so the padding is unobservable; it is left
-            // out because it costs O(depth x qubits) memory and time (16 MB for the 1000-qubit GHZ chain).
+        // The reference pads waiting lines with a nullptr per sweep (Network.h:1102-1104).  Every reader of
+        // mNodesByWire skips nullptr entries (Network.h:1179,1217), so the padding is unobservable; it is left
+        // out because it costs O(depth x qubits) memory and time (16 MB for the 1000-qubit GHZ chain).
+        for (int q : movedLines) {
+            if (!advanced[q]) continue;                           // (a line can be listed twice)
+            if (fusedThisSweep && !merged[q].empty()) merged[q].back() = head[q];
+            else merged[q].push_back(head[q]);
+            advanced[q] = 0;
         }
         fusedThisSweep = false;
-        if (!any) break;
-        // finished lines can never advance again: drop them (they were skipped by the first test anyway)
-        size_t keep = 0;
-        for (int q : active) if (cursor[q] < static_cast<int>(mNodesByWire[q].size())) active[keep++] = q;
-        active.resize(keep);
+        // who can possibly advance in the next sweep: the lines that moved, and both lines of the node each now faces
+        next.clear();
+        auto enqueue = [&](int q) { if (q >= 0 && q < nq && !queued[q] && pending(q)) { queued[q] = 1; next.push_back(q); } };
+        for (int q : movedLines) {
+            enqueue(q);
+            if (pending(q)) {
+                Node *front = mNodesByWire[q][cursor[q]].get();
+                if (front->mRank != 1) { enqueue(front->GetWireNumber()[0]); enqueue(front->GetWireNumber()[1]); }
+            }
+        }
+        std::sort(next.begin(), next.end());
+        for (int q : next) queued[q] = 0;
+        visit.swap(next);
     }
     mNodesByWire = std::move(merged);
 }
@@ -658,7 +714,7 @@ inline void Network::OutputCircuitToVisualGraph(const std::string &toOutputTo) c
     out << "graph " << mInputFile.substr(0, mInputFile.find('.')) << "{" << std::endl;
     out << "node [height=1, width=.1];\n rankdir=LR;" << std::endl;
     int next = 0;
-    for (const auto &n : mUncontractedNodes) {
+    for (const auto &n : GetUncontractedNodes()) {
         out << "node" << next << " [label=\"" << n->GetTypeOfNodeString() << "\"";
         if (n->mRank == 1) out << ", height = .5";
         out << "];" << std::endl;
@@ -684,7 +740,7 @@ inline void Network::OutputCircuitToTreewidthGraph(const std::string &toOutputTo
     out << "c Created From File: " << mInputFile << std::endl;
     std::unordered_map<std::shared_ptr<Node>, int> number;
     int next = 0;
-    for (const auto &n : mUncontractedNodes) number.insert({n, next++});
+    for (const auto &n : GetUncontractedNodes()) number.insert({n, next++});
     for (size_t l = 0; l < mNodesByWire.size(); ++l) {
         const auto &line = mNodesByWire[l];
         size_t prev = 0;

@@ -103,6 +103,7 @@ public:
     bool mContracted;
     std::pair<int, int> mCreatedFrom{0, 0};
     bool mSelectedInCostContractionAlgorithm;
+    int mLiveSlot{-1};                 // addition: position in the owning Network's list of uncontracted nodes (-1: not listed)
 
     std::vector<std::shared_ptr<Wire>> &GetWires() {
         if (static_cast<int>(mWires.size()) > mRank)
