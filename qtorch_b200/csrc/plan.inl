@@ -373,8 +373,9 @@ int qtb_plan_stage_inputs(qtb_ctx *ctx, qtb_plan *pl, int slot, const double *co
     return QTB_OK;
 }
 int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *pl, int slot) {
-    if (!ctx || !pl || slot < 0 || (size_t)slot >= pl->slotDev.size() || !pl->slotDev[slot]) return fail(QTB_ERR_INVALID, "unknown input slot");
+    if (!ctx || !pl) return fail(QTB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    if (slot < 0 || (size_t)slot >= pl->slotDev.size() || !pl->slotDev[slot]) return fail(QTB_ERR_INVALID, "unknown input slot");
     ST(ensure_device(ctx));
     CU(cudaMemcpyAsync(pl->inBlobDev, pl->slotDev[slot], pl->inBlobBytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return plan_run_locked(ctx, pl);
@@ -382,9 +383,9 @@ int qtb_plan_run_device_slot(qtb_ctx *ctx, qtb_plan *pl, int slot) {
 int qtb_plan_run_slots(qtb_ctx *ctx, qtb_plan *pl, const int *slots, int n, double *hostSum, double *hostEach) {
     if (!ctx || !pl || !slots || n < 1 || !hostSum) return fail(QTB_ERR_INVALID, "bad argument");
     if (pl->outRank != 0) return fail(QTB_ERR_INVALID, "slot sums need a scalar plan output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
     for (int j = 0; j < n; j++)
         if (slots[j] < 0 || (size_t)slots[j] >= pl->slotDev.size() || !pl->slotDev[slots[j]]) return fail(QTB_ERR_INVALID, "unknown input slot");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     ST(ensure_device(ctx));
     ST(flush_locked(ctx));
     const size_t nSegs = pl->segs.size(), pre = pl->prefixSegs;
