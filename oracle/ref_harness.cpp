@@ -23,6 +23,7 @@
 //   stoch qasm measure threads                      ContractionTools::Contract(Stochastic), prints the plan
 //   cost  qasm measure pValue seed threads          ContractionTools::Contract(CostContractSimple, pValue) with the
 //                                                   generator seeded (see the access note below), prints the plan
+//   inp   script.inp                                leviParser on a ">type key value" script, dumps its four maps
 //   user  qasm measure seqfile                      ContractUserDefinedSequenceOfWires
 //   maxcut graph.dgf p outdir b1..bp g1..gp         the body of F_p (src/maxcut.cpp:162-204) for fixed angles: per-edge
 //                                                   light-cone circuits written with the reference's own emitters
@@ -59,6 +60,7 @@
 #define private public
 #include "ContractionTools.h"   // reference header (pulls Network.h, Node.h, LineGraph.h ...)
 #undef private
+#include "leviParser.hpp"       // reference .inp reader (the `inp` mode)
 #include "maxcut.h"             // reference QAOA helpers (ExtraData, circuit emitters); <nlopt.hpp> = oracle/stubs
 
 using namespace qtorch;
@@ -242,6 +244,18 @@ static int mode_cost(int argc, char **argv) {
     return 0;
 }
 
+// inp script.inp: the reference's leviParser on a script, one line per map entry (same format as qtb_harness inp)
+static int mode_inp(int argc, char **argv) {
+    leviParser script;
+    const bool opened = script.readInputFile(argv[2]);
+    printf("@@opened %d\n", opened ? 1 : 0);
+    for (const auto &kv : script.mapString) printf("@@string %s %s\n", kv.first.c_str(), kv.second.c_str());
+    for (const auto &kv : script.mapBool) printf("@@bool %s %d\n", kv.first.c_str(), kv.second ? 1 : 0);
+    for (const auto &kv : script.mapInt) printf("@@int %s %d\n", kv.first.c_str(), kv.second);
+    for (const auto &kv : script.mapDouble) printf("@@double %s %.17g\n", kv.first.c_str(), kv.second);
+    return 0;
+}
+
 static int mode_user(int argc, char **argv) {
     ContractionTools p(argv[2], argv[3]);
     auto net = p.ContractUserDefinedSequenceOfWires(argv[4]);
@@ -291,6 +305,7 @@ int main(int argc, char **argv) {
         if (m == "seq") return mode_seq(argc, argv);
         if (m == "stoch") return mode_stoch(argc, argv);
         if (m == "cost") return mode_cost(argc, argv);
+        if (m == "inp") return mode_inp(argc, argv);
         if (m == "user") return mode_user(argc, argv);
         if (m == "maxcut") return mode_maxcut(argc, argv);
     } catch (std::exception &e) {

@@ -119,6 +119,19 @@ static int mode_cnf(int argc, char **argv) {
     return 0;
 }
 
+// inp script.inp: what the ".inp" reader makes of a script -- one line per map entry, sorted by key
+static int mode_inp(int argc, char **argv) {
+    (void)argc;
+    leviParser script;
+    const bool opened = script.readInputFile(argv[2]);
+    printf("@@opened %d\n", opened ? 1 : 0);
+    for (const auto &kv : script.mapString) printf("@@string %s %s\n", kv.first.c_str(), kv.second.c_str());
+    for (const auto &kv : script.mapBool) printf("@@bool %s %d\n", kv.first.c_str(), kv.second ? 1 : 0);
+    for (const auto &kv : script.mapInt) printf("@@int %s %d\n", kv.first.c_str(), kv.second);
+    for (const auto &kv : script.mapDouble) printf("@@double %s %.17g\n", kv.first.c_str(), kv.second);
+    return 0;
+}
+
 static int mode_seq(int argc, char **argv, bool steps) {
     const char *qasm = argv[2], *meas = argv[3], *planf = argv[4];
     std::vector<std::pair<int, int>> plan;
@@ -181,6 +194,7 @@ int main(int argc, char **argv) {
         if (m == "gate") return mode_gate(argc, argv);
         if (m == "lg") return mode_lg(argc, argv, steps);
         if (m == "cnf") return mode_cnf(argc, argv);
+        if (m == "inp") return mode_inp(argc, argv);
         if (m == "minfill") return mode_minfill(argc, argv, steps);
         if (m == "seq") return mode_seq(argc, argv, steps);
         if (m == "stoch") return mode_stoch(argc, argv, steps);

@@ -137,3 +137,22 @@ def test_exported_plan_evaluated_by_oracle_matches_reference_value(built, name):
         rk.append(rk[a] + rk[b] - 2 * len(pa))
     ref = complex(*rec["value"])
     assert abs(complex(t[-1][0]) - ref) <= 1e-12 * max(1.0, abs(ref))
+
+
+def test_inp_script_reader_matches_reference(built):
+    """the ".inp" reader (host/leviParser.hpp): the four maps it fills from a script with comments, every accepted bool
+    spelling class, a bad bool, an unknown type and a directive after free text -- against the dump the reference's
+    leviParser produced for the same file (tests/golden/scripts/reader_cases.expected), and live when it is built"""
+    script = os.path.join(GOLDEN, "scripts", "reader_cases.inp")
+    want = open(os.path.join(GOLDEN, "scripts", "reader_cases.expected")).read().split("\n")
+    want = [l for l in want if l]
+    import subprocess
+    got = subprocess.run([qt.HARNESS_PATH, "inp", script], capture_output=True, text=True, timeout=60,
+                         env=dict(os.environ, QTORCH_PLAN_ONLY="1", QTORCH_QUIET="1")).stdout.splitlines()
+    assert [l for l in got if l.startswith("@@")] == want
+    if O.ref_available():
+        ref = subprocess.run([O.ref_harness_path(), "inp", script], capture_output=True, text=True, timeout=60).stdout.splitlines()
+        assert [l for l in ref if l.startswith("@@")] == want
+    missing = subprocess.run([qt.HARNESS_PATH, "inp", os.path.join(GOLDEN, "scripts", "no_such_file.inp")], capture_output=True, text=True,
+                             timeout=60, env=dict(os.environ, QTORCH_PLAN_ONLY="1", QTORCH_QUIET="1")).stdout
+    assert "@@opened 0" in missing
