@@ -90,6 +90,11 @@ int qtb_read_scalar_end(qtb_ctx *ctx, qtb_scalar_read *read, double out_re_im[2]
  * and grouped into one launch until the next flush/sync/download.  rank(C) must equal
  * rank(A)+rank(B)-2k.  k = 0 is accepted (outer product; the reference only reaches it for two rank-0
  * nodes, Network.h:772).                                                                             */
+/* Tensors are SINGLE-USE as operands, like the reference's nodes (mContracted, Network.h:719-723): a big tile-kernel step
+ * whose result is immediately contracted with another tensor over all of its legs runs fused with that inner product and
+ * its intermediate is never written -- the intermediate's handle then holds no data and any later use of it returns
+ * QTB_ERR_EMPTY_INPUT.  a == b and c == a / c == b are rejected (QTB_ERR_INVALID).  An output or upload target that
+ * deferred steps still read or write is ordered after them.                                                          */
 int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k,
                  const int *pos_a, const int *pos_b, qtb_tensor c);
 

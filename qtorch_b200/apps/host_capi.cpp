@@ -146,8 +146,7 @@ int qth_export_plan_linegraph(const char *qasm, const char *measure, const char 
             lg.SetQBBOutFiles("/dev/null", qbbOut, "/dev/null");
         } else {
             // no frozen QuickBB file: in-process min-fill ordering (LineGraph::runMinFill)
-            const std::string tmp = "/tmp/qtb_minfill_" + std::to_string(static_cast<long>(getpid())) + ".out";
-            lg.SetQBBOutFiles("/dev/null", tmp, "/dev/null");
+            lg.SetQBBOutFiles("/dev/null", "", "/dev/null");          // ordering handed over in memory, no temp file
             lg.runMinFill();
         }
         if (!lg.LGContract()) rc = 2;

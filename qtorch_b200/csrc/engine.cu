@@ -392,6 +392,7 @@ struct qtb_ctx_s {
     std::vector<PendingUpload> pendingUploads;
     std::vector<uint8_t> payload;
     std::unordered_map<const void *, uint32_t> producedLevel;     // tensor buffer -> level of the pending step writing it
+    std::unordered_map<const void *, uint32_t> readLevel;         // tensor buffer -> highest level of a pending step READING it
     std::vector<std::pair<int, void *>> deferredFrees;            // (rank, ptr) released after the next flush
     // stats / trace
     qtb_stats stats{};
@@ -639,7 +640,7 @@ static int flush_locked(qtb_ctx *ctx) {
     if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, 0, 0, (int)ctx->pending.size(), KIND_MICRO}); }
     ctx->stats.launches++;
     ctx->stats.micro_steps += (long long)ctx->pending.size();
-    ctx->pending.clear(); ctx->pendingUploads.clear(); ctx->payload.clear(); ctx->producedLevel.clear();
+    ctx->pending.clear(); ctx->pendingUploads.clear(); ctx->payload.clear(); ctx->producedLevel.clear(); ctx->readLevel.clear();
     for (auto &f : ctx->deferredFrees) ctx->pool.release(f.first, f.second);
     ctx->deferredFrees.clear();
     return QTB_OK;
@@ -735,18 +736,12 @@ int qtb_device_count(int *count) {
     return QTB_OK;
 }
 
-int qtb_ctx_create(int device, qtb_ctx **out) {
-    if (!out) return fail(QTB_ERR_INVALID, "null out");
-    *out = nullptr;
-    int n = 0;
-    ST(qtb_device_count(&n));
-    if (device < 0 || device >= n) return fail(QTB_ERR_INVALID, "device index out of range");
-    qtb_ctx *ctx = new qtb_ctx_s();
+static int ctx_init(qtb_ctx *ctx, int device) {
     ctx->device = device;
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) { delete ctx; return fail(QTB_ERR_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only"); }
+    if (prop.major != 10) return fail(QTB_ERR_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only");
     ctx->numSMs = prop.multiProcessorCount;
     if (const char *e = getenv("QTB_MICRO_LOG4")) ctx->microLog4 = std::max(0, std::min(8, atoi(e)));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -765,6 +760,23 @@ int qtb_ctx_create(int device, qtb_ctx **out) {
         inst.occ = std::max(1, occ);
     }
     CU(cudaDeviceSynchronize());
+    return QTB_OK;
+}
+
+int qtb_ctx_create(int device, qtb_ctx **out) {
+    if (!out) return fail(QTB_ERR_INVALID, "null out");
+    *out = nullptr;
+    int n = 0;
+    ST(qtb_device_count(&n));
+    if (device < 0 || device >= n) return fail(QTB_ERR_INVALID, "device index out of range");
+    qtb_ctx *ctx = new qtb_ctx_s();
+    const int st = ctx_init(ctx, device);
+    if (st != QTB_OK) {                      // give back whatever a half-built context holds (the error text survives)
+        const std::string keep = g_lastError;
+        qtb_ctx_destroy(ctx);
+        g_lastError = keep;
+        return st;
+    }
     *out = ctx;
     return QTB_OK;
 }
@@ -772,7 +784,7 @@ int qtb_ctx_create(int device, qtb_ctx **out) {
 int qtb_ctx_destroy(qtb_ctx *ctx) {
     if (!ctx) return QTB_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->commBuf) cudaFree(ctx->commBuf);
     for (auto &t : ctx->traceRecs) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
@@ -781,9 +793,16 @@ int qtb_ctx_destroy(qtb_ctx *ctx) {
     for (cudaEvent_t e : ctx->auxEvents) cudaEventDestroy(e);
     if (ctx->forkEvent) cudaEventDestroy(ctx->forkEvent);
     for (qtb_scalar_read_s *r : ctx->freeReads) { cudaFreeHost(r->pinned); cudaEventDestroy(r->done); delete r; }
-    cudaFreeHost(ctx->ringHost); cudaFree(ctx->ringDev); cudaFreeHost(ctx->scalarPinned); cudaFree(ctx->zeroOffsetDev); cudaFree(ctx->reduceScratch);
-    cudaEventDestroy(ctx->ringEvent);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->ringHost) cudaFreeHost(ctx->ringHost);
+    if (ctx->ringDev) cudaFree(ctx->ringDev);
+    if (ctx->scalarPinned) cudaFreeHost(ctx->scalarPinned);
+    if (ctx->zeroOffsetDev) cudaFree(ctx->zeroOffsetDev);
+    if (ctx->reduceScratch) cudaFree(ctx->reduceScratch);
+    if (ctx->batchOut) cudaFreeHost(ctx->batchOut);
+    if (ctx->ringEvent) cudaEventDestroy(ctx->ringEvent);
+    if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
     delete ctx;
     return QTB_OK;
 }
@@ -836,7 +855,10 @@ int qtb_tensor_upload(qtb_ctx *ctx, qtb_tensor t, const double *host) {
     const size_t bytes = Pool::bytes(t->rank);
     if (t->rank <= 5 && !disable_micro()) {
         // rides in the next grouped launch as a level-0 copy item (one H2D for the whole batch)
-        if (ctx->payload.size() + bytes > ((size_t)8 << 20) || ctx->pending.size() + ctx->pendingUploads.size() >= 8192) ST(flush_locked(ctx));
+        // Upload copies run at level 0 of the grouped launch: a buffer that a pending step still reads or writes must not be
+        // overwritten there (re-uploading angles into a live handle), so such an upload starts a new batch.
+        if (ctx->payload.size() + bytes > ((size_t)8 << 20) || ctx->pending.size() + ctx->pendingUploads.size() >= 8192 ||
+            ctx->producedLevel.count(t->d) || ctx->readLevel.count(t->d)) ST(flush_locked(ctx));
         const size_t off = ctx->payload.size();
         ctx->payload.resize(off + bytes);
         memcpy(ctx->payload.data() + off, host, bytes);
@@ -920,6 +942,7 @@ int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos
     ST(make_geom(a->rank, b->rank, k, pos_a, pos_b, g));
     if (g.rC != c->rank) return fail(QTB_ERR_INVALID, "rank(C) != rank(A)+rank(B)-2k");
     if (c == a || c == b) return fail(QTB_ERR_INVALID, "output aliases an operand");
+    if (a == b) return fail(QTB_ERR_INVALID, "a tensor cannot be contracted with itself (a step joins two distinct nodes, Network.h:715-716)");
     ST(ensure_device(ctx));
     ST(ensure_buffer(ctx, c));
     GettChoice gc{0, false};
@@ -934,9 +957,19 @@ int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos
         if (ia != ctx->producedLevel.end()) lvl = std::max(lvl, ia->second + 1);
         auto ib = ctx->producedLevel.find(b->d);
         if (ib != ctx->producedLevel.end()) lvl = std::max(lvl, ib->second + 1);
+        // an output buffer that pending steps still read (write-after-read) or write (write-after-write: out= re-used, or a
+        // level-0 upload copy) is rewritten only after them
+        auto ir = ctx->readLevel.find(c->d);
+        if (ir != ctx->readLevel.end()) lvl = std::max(lvl, ir->second + 1);
+        auto iw = ctx->producedLevel.find(c->d);
+        if (iw != ctx->producedLevel.end()) lvl = std::max(lvl, iw->second + 1);
         ps.level = lvl;
         ctx->pending.push_back(ps);
         ctx->producedLevel[c->d] = lvl;
+        for (const void *src : {(const void *)a->d, (const void *)b->d}) {
+            auto it = ctx->readLevel.find(src);
+            if (it == ctx->readLevel.end()) ctx->readLevel[src] = lvl; else it->second = std::max(it->second, lvl);
+        }
         if (ctx->pending.size() >= 8192) ST(flush_locked(ctx));
     } else if (ctx->held.active && kind == KIND_REDUCE && (a->d == ctx->held.C || b->d == ctx->held.C) &&
                fusable_pair(ctx->held.g, KIND_GETT, ctx->held.gc, g, a->d == ctx->held.C)) {
@@ -948,6 +981,7 @@ int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
         ST(enqueue_fused(ctx, h.g, h.gc, h.A, h.B, g, tIsA, tIsA ? b->d : a->d, c->d, ctx->stream));
+        (tIsA ? a : b)->hasData = false;          // the intermediate was never written: any later use of it reports EMPTY_INPUT
         if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, h.g.rA, h.g.rB, h.g.k, KIND_FUSED}); }
         for (auto &f : ctx->deferredFrees) ctx->pool.release(f.first, f.second);
         ctx->deferredFrees.clear();

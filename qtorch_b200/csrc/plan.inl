@@ -440,6 +440,8 @@ int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const dou
     for (int i = 0; i < n; i++) {
         if (!plans[i] || plans[i]->outRank != 0) return fail(QTB_ERR_INVALID, "batched plans must have scalar outputs");
         if (plans[i]->segs.size() != 1 || !plans[i]->segs[0].micro) allMicro = false;
+        // one plan = one set of buffers and one graph: the same plan twice in a batch would race with itself
+        for (int j = 0; j < i; j++) if (plans[j] == plans[i]) return fail(QTB_ERR_INVALID, "the same plan appears twice in one batch");
     }
     for (int i = 0; i < n; i++) ST(plan_upload_locked(ctx, plans[i], hostInputs[i]));
     if (allMicro) {

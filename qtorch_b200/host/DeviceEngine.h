@@ -10,6 +10,7 @@
 // planner logic can be tested and plans exported on machines without a GPU; it is NOT a CPU fallback --
 // tensors have no data in that mode and every value read returns NaN.
 #pragma once
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <chrono>
@@ -83,7 +84,7 @@ private:
 // mpirun wrappers, a shell loop): joins the job's NCCL communicator and hands back the scalar allreduce the term
 // dispatcher needs (edges dealt round-robin, ONE ncclAllReduce of the partial objective per evaluation).
 // The NCCL unique id travels through a file: rank 0 writes it (atomically), the others wait for it.  Path:
-// QTORCH_NCCL_ID_FILE, else /tmp/qtorch_nccl_id.<MASTER_PORT or 0>.  Single-process runs (WORLD_SIZE unset or 1) skip
+// QTORCH_NCCL_ID_FILE, else /tmp/qtorch-<uid>/nccl_id.<MASTER_PORT or 0>.<QTORCH_JOB_ID or launcher pid>.  Single-process runs (WORLD_SIZE unset or 1) skip
 // all of this and get an empty functor.
 struct Job {
     int rank = 0, world = 1;
@@ -95,24 +96,39 @@ struct Job {
         if (const char *r = std::getenv("RANK")) job.rank = std::atoi(r);
         if (job.world == 1) { job.rank = 0; return job; }
         if (job.rank < 0 || job.rank >= job.world) throw DeviceUnavailable("RANK outside [0, WORLD_SIZE)");
+        // The id file lives in a per-user directory (mode 0700) and carries a job nonce in its name -- QTORCH_JOB_ID, else
+        // the launcher's pid (all ranks of one torchrun / shell loop share their parent) -- so neither another user nor a
+        // job that died a moment ago can hand this job a stale id.  Rank 0 removes any leftover and creates the file
+        // exclusively (O_EXCL) before publishing it by rename.
         std::string path;
         if (const char *f = std::getenv("QTORCH_NCCL_ID_FILE")) path = f;
-        else { const char *port = std::getenv("MASTER_PORT"); path = std::string("/tmp/qtorch_nccl_id.") + (port ? port : "0"); }
+        else {
+            const std::string dir = "/tmp/qtorch-" + std::to_string(static_cast<long>(getuid()));
+            mkdir(dir.c_str(), 0700);
+            struct stat ds;
+            if (stat(dir.c_str(), &ds) != 0 || ds.st_uid != getuid() || (ds.st_mode & 077) != 0)
+                throw DeviceUnavailable("NCCL id directory " + dir + " is not private to this user");
+            const char *port = std::getenv("MASTER_PORT"), *jid = std::getenv("QTORCH_JOB_ID");
+            path = dir + "/nccl_id." + (port ? port : "0") + "." + (jid ? std::string(jid) : std::to_string(static_cast<long>(getppid())));
+        }
         char id[QTB_UNIQUE_ID_BYTES];
         if (job.rank == 0) {
             check(qtb_comm_unique_id(id));
             const std::string tmp = path + ".tmp." + std::to_string(static_cast<long>(getpid()));
-            { std::ofstream out(tmp, std::ios::binary); out.write(id, QTB_UNIQUE_ID_BYTES); }
+            std::remove(path.c_str());
+            std::remove(tmp.c_str());
+            const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0600);
+            if (fd < 0 || write(fd, id, QTB_UNIQUE_ID_BYTES) != QTB_UNIQUE_ID_BYTES) { if (fd >= 0) close(fd); throw DeviceUnavailable("cannot write the NCCL id at " + tmp); }
+            close(fd);
             if (std::rename(tmp.c_str(), path.c_str()) != 0) throw DeviceUnavailable("cannot publish the NCCL id at " + path);
         } else {
-            // a file left behind by a job that died is older than this process: only an id published within the last
-            // 30 s before this rank started (launchers start ranks together) or later is accepted
+            // belt and braces: an id older than 30 s before this rank started is not from this launch
             const time_t notBefore = time(nullptr) - 30;
             bool got = false;
             for (int tries = 0; tries < 1200 && !got; ++tries) {            // up to 60 s
                 struct stat st;
                 std::ifstream in(path, std::ios::binary);
-                if (stat(path.c_str(), &st) == 0 && st.st_mtime >= notBefore && in && in.read(id, QTB_UNIQUE_ID_BYTES)) got = true;
+                if (stat(path.c_str(), &st) == 0 && st.st_uid == getuid() && st.st_mtime >= notBefore && in && in.read(id, QTB_UNIQUE_ID_BYTES)) got = true;
                 else std::this_thread::sleep_for(std::chrono::milliseconds(50));
             }
             if (!got) throw DeviceUnavailable("no NCCL id from rank 0 at " + path);

@@ -68,12 +68,16 @@ private:
     std::string cnfName = "output/lg.cnf";
     std::string qbbOutName = "output/qbb.out";
     std::string qbbStatsName = "output/qbb-stats.out";
+    std::vector<int> memOrder;                                        // last runMinFill() order, 1-based
+    bool haveMemOrder = false;
 };
 
 inline void LineGraph::Build(std::shared_ptr<Network> net) {
     origNetwork = net;
     GraphWires.clear();
     LGEdges.clear();
+    memOrder.clear();
+    haveMemOrder = false;
     std::unordered_map<Wire *, int> seen;
     const std::vector<std::shared_ptr<Node>> nodes = net->GetUncontractedNodes();
     for (const auto &node : nodes) {
@@ -168,25 +172,38 @@ inline int LineGraph::runMinFill(int trials, unsigned seed) {
         }
         if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestWidth = width; bestOrder = order; }
     }
-    mkdir("output", 0755);
-    std::ofstream out(qbbOutName);
-    out << " The treewidth of the graph in the file " << cnfName << " is " << bestWidth << " (greedy min-fill, in-process)" << std::endl;
-    out << " The optimal ordering is " << std::endl;
-    for (int v : bestOrder) out << v + 1 << " ";
-    out << std::endl;
+    // the order stays in memory for LGContract(); it is also written in QuickBB's format unless the caller asked for
+    // no file at all (SetQBBOutFiles with an empty qbb.out name)
+    memOrder.clear();
+    for (int v : bestOrder) memOrder.push_back(v + 1);
+    haveMemOrder = true;
+    if (!qbbOutName.empty()) {
+        if (qbbOutName.compare(0, 7, "output/") == 0) mkdir("output", 0755);
+        std::ofstream out(qbbOutName);
+        out << " The treewidth of the graph in the file " << cnfName << " is " << bestWidth << " (greedy min-fill, in-process)" << std::endl;
+        out << " The optimal ordering is " << std::endl;
+        for (int v : bestOrder) out << v + 1 << " ";
+        out << std::endl;
+    }
     return bestWidth;
 }
 
 inline bool LineGraph::LGContract() {
-    std::ifstream fQbb(qbbOutName);
-    if (!fQbb) {
-        std::cout << "Unable to open qbb file: " << qbbOutName << std::endl;
-        throw QbbFailure();
-    }
     std::vector<int> order;
     std::string line;
     bool found = false;
-    while (std::getline(fQbb, line)) {
+    std::ifstream fQbb;
+    if (qbbOutName.empty() && haveMemOrder) {          // in-process ordering that never touched the file system
+        order = memOrder;
+        found = true;
+    } else {
+        fQbb.open(qbbOutName);
+        if (!fQbb) {
+            std::cout << "Unable to open qbb file: " << qbbOutName << std::endl;
+            throw QbbFailure();
+        }
+    }
+    while (!found && std::getline(fQbb, line)) {
         if (line != " The optimal ordering is ") continue;
         std::getline(fQbb, line);
         std::stringstream ss(line);

@@ -341,11 +341,9 @@ inline std::vector<bool> maxcutGetFinalString(const std::string &graphFilePath, 
         if (contractionSequence.empty()) {
             net->ReduceCircuit();
             LineGraph lg(net);
-            const std::string tmp = "/tmp/qtb_finalstring_" + std::to_string(reinterpret_cast<uintptr_t>(net.get())) + ".out";
-            lg.SetQBBOutFiles("/dev/null", tmp, "/dev/null");
+            lg.SetQBBOutFiles("/dev/null", "", "/dev/null");          // ordering handed over in memory, no temp file
             lg.runMinFill();
             lg.LGContract();
-            std::remove(tmp.c_str());
         } else {
             ContractionTools tools(net);
             tools.ContractGivenSequence(contractionSequence);

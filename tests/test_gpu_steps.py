@@ -334,3 +334,53 @@ def test_tile_kernels_without_the_streaming_class():
                         "gett_steps or random_leg_maps or streaming_apply_steps"],
                        capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_deferred_steps_respect_reuse_of_buffers(engine):
+    """Deferred micro-steps are levelled by dependency inside ONE grouped launch.  Rewriting a buffer that pending steps
+    still read or write -- re-uploading a gate's angles into a live handle, re-using out= -- must be ordered after them
+    (write-after-read / write-after-write), not scheduled side by side at level 0."""
+    rng = np.random.default_rng(77)
+    s0 = rng.standard_normal(4) + 1j * rng.standard_normal(4)
+    g1, g2 = (rng.standard_normal(16) + 1j * rng.standard_normal(16) for _ in range(2))
+    ts, tg = engine.tensor(1, s0), engine.tensor(2, g1)
+    c1 = engine.contract(ts, tg, [0], [0])                 # pending: reads tg (= g1)
+    tg.upload(g2)                                          # same handle, new contents, while c1 is still deferred
+    c2 = engine.contract(ts, tg, [0], [0])
+    r1, r2 = c1.download(), c2.download()
+    assert np.abs(r1 - O.contract(s0, 1, g1, 2, [0], [0])).max() < 1e-13
+    assert np.abs(r2 - O.contract(s0, 1, g2, 2, [0], [0])).max() < 1e-13
+    # out= re-used: the second write lands after the step that reads the first result
+    out = engine.tensor(1)
+    engine.contract(ts, tg, [0], [0], out=out)             # out = s0 . g2
+    d1 = engine.contract(out, tg, [0], [0])                # reads out
+    tg2 = engine.tensor(2, g1)
+    engine.contract(ts, tg2, [0], [0], out=out)            # rewrites out while d1 is pending
+    want_d1 = O.contract(O.contract(s0, 1, g2, 2, [0], [0]), 1, g2, 2, [0], [0])
+    assert np.abs(d1.download() - want_d1).max() < 1e-13
+    assert np.abs(out.download() - O.contract(s0, 1, g1, 2, [0], [0])).max() < 1e-13
+    for t in (ts, tg, tg2, c1, c2, out, d1):
+        t.free()
+
+
+def test_fused_intermediate_is_single_use(engine):
+    """the eager fused path never writes the big intermediate: its handle must say so instead of serving pool garbage;
+    self-contraction is rejected like in plans"""
+    A, B, D = _rand(7, 41), _rand(7, 42), _rand(10, 43)
+    ta, tb, td = engine.tensor(7, A), engine.tensor(7, B), engine.tensor(10, D)
+    tt = engine.contract(ta, tb, [0, 3], [5, 1])
+    out = engine.contract(tt, td, list(range(10)), list(range(10)))
+    O.lib().qto_set_threads(8)
+    ref = O.contract(O.contract(A, 7, B, 7, [0, 3], [5, 1]), 10, D, 10, list(range(10)), list(range(10)))[0]
+    assert abs(out.scalar() - ref) <= 1e-11 * max(1.0, abs(ref))
+    with pytest.raises(qt.EngineError) as e:
+        tt.download()
+    assert e.value.status == 3
+    with pytest.raises(qt.EngineError) as e:
+        engine.contract(tt, td, list(range(10)), list(range(10)))
+    assert e.value.status == 3
+    with pytest.raises(qt.EngineError) as e:
+        engine.contract(ta, ta, [0], [1])
+    assert e.value.status == 2
+    for t in (ta, tb, td, tt, out):
+        t.free()
