@@ -136,6 +136,26 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int n_inputs, const int *input_ranks, i
 int qtb_plan_run_slots(qtb_ctx *ctx, qtb_plan *plan, const int *slots, int n, double *host_sum, double *host_each);
 /* sum of 4^(rC+k) over the invariant prefix (done once per qtb_plan_run_slots call, not once per slot) */
 long long qtb_plan_prefix_units(qtb_plan *plan);
+
+/* The sliced-amplitude executor: the same sliced plan, but an amplitude never synchronises with the host while it runs.
+ * `n_lanes` (1..8) replicas of the plan (own buffers, graphs and stream) share a rank's slices, so that two big launches
+ * are always queued (one slice's tile kernel takes over each SM the previous one has left) and the invariant prefix of
+ * the next amplitude overlaps the slices of the current one.  qtb_sliced_begin enqueues everything and returns at once:
+ * prefix per used lane, the suffix per listed slot, slot scalars accumulated on the device in a fixed order, then -- if
+ * `allreduce` is non-zero (needs qtb_comm_init) -- ONE in-stream ncclAllReduce of the complex scalar (replaces
+ * f_pVal += ..., maxcut.cpp:196, across ranks) and the 16-byte device->host copy.  qtb_read_scalar_end waits for that
+ * copy.  n = 0 is legal (a rank that owns no slice still joins the reduction).  A slot may be re-staged only after the
+ * amplitudes that used it have been read; staging goes through its own upload stream.                               */
+typedef struct qtb_sliced_s qtb_sliced;
+int qtb_sliced_create(qtb_ctx *ctx, int n_inputs, const int *input_ranks, int n_steps, const qtb_plan_step *steps,
+                      int n_invariant_steps, int n_lanes, qtb_sliced **out);
+int qtb_sliced_destroy(qtb_ctx *ctx, qtb_sliced *sliced);
+int qtb_sliced_stage(qtb_ctx *ctx, qtb_sliced *sliced, int slot, const double *const *host_inputs);
+int qtb_sliced_begin(qtb_ctx *ctx, qtb_sliced *sliced, const int *slots, int n, int allreduce, qtb_scalar_read **out);
+int qtb_sliced_lanes(qtb_sliced *sliced);
+long long qtb_sliced_units(qtb_sliced *sliced);            /* per slice, prefix included */
+long long qtb_sliced_prefix_units(qtb_sliced *sliced);
+int qtb_sliced_launches(qtb_sliced *sliced, int *prefix_launches);   /* kernel launches of one slice (prefix included) */
 /* Grouped evaluation of n independent plans with scalar outputs (e.g. the 45 per-edge <ZiZj> networks of one QAOA
  * objective evaluation, maxcut.cpp:171-198): all inputs are uploaded, plans that consist of micro-steps only run in
  * ONE launch (one CTA per plan), the n scalars come back with one synchronisation.
@@ -154,6 +174,8 @@ int qtb_comm_destroy(qtb_ctx *ctx);
 /* In-place sum over ranks of n complex scalars held in HOST memory (staged through the ctx stream,
  * one ncclAllReduce over NVLink).                                                                     */
 int qtb_allreduce_sum(qtb_ctx *ctx, double *host_re_im, int n_complex);
+/* The same sum on n complex scalars that already live in DEVICE memory: enqueued on the ctx stream, returns at once. */
+int qtb_allreduce_sum_device(qtb_ctx *ctx, void *device_re_im, int n_complex);
 
 /* ---- introspection (bench.py: gpu_launches, roofline bookkeeping) --------------------------------- */
 typedef struct qtb_stats {

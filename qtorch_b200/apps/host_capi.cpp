@@ -7,6 +7,7 @@
 #include <unistd.h>
 #include <chrono>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -166,6 +167,125 @@ int qth_export_plan_linegraph(const char *qasm, const char *measure, const char 
     }
     device::Engine::SetPlanOnly(before);
     return rc;
+}
+
+// ---- index slicing (host/Slicing.h) ------------------------------------------------------------------------------------
+// planner only (no device): cut `nWires` wires of a plan given in qtb_plan_step layout.  Buffers are owned by the library
+// until the next call on this thread.  wires / cuts use the label encoding of Slicing.h (input tensor * 32 + leg).
+struct QthSlicedPlan {
+    int nInputs, nSteps, nInvariant, nWires, peakRank, nCuts;
+    const int *inputRanks;          // ranks of ONE slice's inputs
+    const qtb_plan_step *steps;     // hoisted sliced plan
+    const int *wires;               // nWires labels
+    const int *cuts;                // nCuts triples (input tensor, leg, wire label)
+    double unitsPerSlice, unitsInvariant;
+};
+static thread_local std::vector<int> t_sRanks, t_sWires, t_sCuts;
+static thread_local std::vector<qtb_plan_step> t_sSteps;
+
+static slicing::Plan planFromAbi(int nInputs, const int *ranks, int nSteps, const qtb_plan_step *steps) {
+    slicing::Plan p;
+    p.inputRanks.assign(ranks, ranks + nInputs);
+    for (int i = 0; i < nSteps; i++) {
+        slicing::Step s{steps[i].a, steps[i].b, {}, {}};
+        for (int j = 0; j < steps[i].k; j++) { s.posA.push_back(steps[i].pos_a[j]); s.posB.push_back(steps[i].pos_b[j]); }
+        p.steps.push_back(s);
+    }
+    return p;
+}
+
+int qth_slice_plan(int nInputs, const int *ranks, int nSteps, const qtb_plan_step *steps, int nWires, QthSlicedPlan *out) {
+    try {
+        const slicing::Plan plan = planFromAbi(nInputs, ranks, nSteps, steps);
+        const slicing::SlicedPlan sp = slicing::SlicePlan(plan, slicing::ChooseWires(plan, nWires));
+        t_sRanks = sp.plan.inputRanks;
+        t_sSteps = slicing::ToAbiSteps(sp.plan);
+        t_sWires = sp.wires;
+        t_sCuts.clear();
+        for (const auto &c : sp.cuts) for (const auto &lw : c.second) { t_sCuts.push_back(c.first); t_sCuts.push_back(lw.first); t_sCuts.push_back(lw.second); }
+        out->nInputs = nInputs; out->nSteps = static_cast<int>(t_sSteps.size()); out->nInvariant = sp.nInvariant;
+        out->nWires = static_cast<int>(sp.wires.size()); out->peakRank = sp.peakRank; out->nCuts = static_cast<int>(t_sCuts.size() / 3);
+        out->inputRanks = t_sRanks.data(); out->steps = t_sSteps.data(); out->wires = t_sWires.data(); out->cuts = t_sCuts.data();
+        out->unitsPerSlice = static_cast<double>(sp.unitsPerSlice); out->unitsInvariant = static_cast<double>(sp.unitsInvariant);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+
+// one input tensor's slice (host only): legs[i] fixed to digits[i]
+int qth_slice_tensor(const double *full, int rank, const int *legs, const int *digits, int nCut, double *out) {
+    try {
+        std::vector<std::complex<double>> f(static_cast<size_t>(1) << (2 * rank));
+        memcpy(f.data(), full, f.size() * 16);
+        std::vector<std::pair<int, int>> cut;
+        for (int i = 0; i < nCut; i++) cut.push_back({legs[i], digits[i]});
+        const auto r = slicing::SliceTensor(f, rank, cut);
+        memcpy(out, r.data(), r.size() * 16);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+
+// A line-graph network, index-sliced over the ranks of the job and run by the sliced-amplitude executor.  The host
+// bookkeeping (parse, ReduceCircuit, ordering walk) runs once in plan-only mode; the caller's communicator must already be
+// initialised on the host mirror's engine context when world > 1 (qtb_comm_init on qth_engine_ctx()).
+struct QthSliced {
+    std::unique_ptr<SlicedContraction> run;
+    SlicedContraction::Tensors inputs;
+    long long flopsUnsliced = 0;
+};
+
+void *qth_sliced_create(const char *qasm, const char *measure, const char *qbbOut, int reduce, int nSliceWires, int lanes, int rank, int world) {
+    const bool before = device::Engine::PlanOnly();
+    device::Engine::SetPlanOnly(true);
+    QthSliced *h = new QthSliced();
+    slicing::Plan plan;
+    try {
+        auto net = std::make_shared<Network>(qasm, measure);
+        for (int i = 0; i < net->GetNumOriginalNodes(); i++) h->inputs.push_back(net->GetAllNodes()[i]->GetTensorVals());
+        if (reduce) net->ReduceCircuit();
+        LineGraph lg(net);
+        if (qbbOut && qbbOut[0]) lg.SetQBBOutFiles("/dev/null", qbbOut, "/dev/null");
+        else { lg.SetQBBOutFiles("/dev/null", "", "/dev/null"); lg.runMinFill(); }
+        lg.LGContract();
+        plan = slicing::PlanOfNetwork(*net);
+        h->flopsUnsliced = net->getNumFloatOps();
+    } catch (std::exception &e) {
+        g_err = e.what();
+        device::Engine::SetPlanOnly(before);
+        delete h;
+        return nullptr;
+    }
+    device::Engine::SetPlanOnly(before);
+    try {
+        device::Job job;
+        job.rank = rank; job.world = world;
+        h->run.reset(new SlicedContraction(plan, nSliceWires, job, lanes));
+    } catch (std::exception &e) { g_err = e.what(); delete h; return nullptr; }
+    return h;
+}
+void qth_sliced_destroy(void *h) { delete static_cast<QthSliced *>(h); }
+// info[0..7]: slices, owned, invariant steps, steps, peak rank of a slice, cut wires, launches per slice, launches of the prefix
+int qth_sliced_info(void *hh, long long *info, double *unitsPerSlice, double *unitsInvariant, long long *flopsUnsliced) {
+    QthSliced *h = static_cast<QthSliced *>(hh);
+    const slicing::SlicedPlan &sp = h->run->Sliced();
+    info[0] = static_cast<long long>(sp.NumSlices()); info[1] = static_cast<long long>(h->run->OwnedSlices().size());
+    info[2] = sp.nInvariant; info[3] = static_cast<long long>(sp.plan.steps.size()); info[4] = sp.peakRank; info[5] = static_cast<long long>(sp.wires.size());
+    int pre = 0;
+    info[6] = h->run->LaunchesPerSlice(&pre); info[7] = pre;
+    *unitsPerSlice = static_cast<double>(sp.unitsPerSlice); *unitsInvariant = static_cast<double>(sp.unitsInvariant);
+    *flopsUnsliced = h->flopsUnsliced;
+    return 0;
+}
+int qth_sliced_stage(void *hh, int bank) {
+    QthSliced *h = static_cast<QthSliced *>(hh);
+    try { h->run->Stage(h->inputs, bank); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int qth_sliced_begin(void *hh, int bank) {
+    QthSliced *h = static_cast<QthSliced *>(hh);
+    try { return h->run->Begin(bank); } catch (std::exception &e) { g_err = e.what(); return -1; }
+}
+int qth_sliced_end(void *hh, int ticket, double value[2]) {
+    QthSliced *h = static_cast<QthSliced *>(hh);
+    try { const std::complex<double> v = h->run->End(ticket); value[0] = v.real(); value[1] = v.imag(); return 0; } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
 
 // ---- QAOA term dispatcher (host/maxcut.h QaoaObjective) -------------------------------------------------------------

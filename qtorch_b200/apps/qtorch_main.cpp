@@ -2,7 +2,13 @@
 // Same script keys, console/result-file lines and exit codes as /root/reference/src/main.cpp:42-309
 // (keys: qasm measurement contractmethod quickbbseconds threads qbbonly readqbbresonly 64bit outputpath
 // user-contract-seq).  New optional keys: ">int device N" selects the GPU, ">string qbbdir DIR/" redirects
-// the lg.cnf / qbb.out / qbb-stats.out files (default output/).
+// the lg.cnf / qbb.out / qbb-stats.out files (default output/), and for the line-graph methods
+//   ">int slicewires N"  index-slice the network over N wires (4^N slices; host/Slicing.h), -1 = as few as give every
+//                        rank a slice;   ">int lanes N"  plan replicas per GPU (default 2).
+// Multi-GPU: start one process per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment (e.g.
+// `torchrun --no-python --nproc-per-node 8 qtorch script.inp`): the slices are dealt round-robin over the ranks, the
+// partial sums meet in one NCCL allreduce, rank 0 alone prints and writes the result file.  With WORLD_SIZE > 1 and no
+// slicewires key, -1 is assumed.
 #include <sys/stat.h>
 #include <fstream>
 #include <iostream>
@@ -30,10 +36,25 @@ int main(int argc, char *argv[]) {
     mkdir("output", 0755);
     if (in.mapInt.count("device")) setenv("QTORCH_DEVICE", std::to_string(in.mapInt["device"]).c_str(), 1);
 
+    // one process per GPU: join the job (NCCL) before anything else; ranks other than 0 stay silent
+    device::Job job;
+    try {
+        job = device::Job::FromEnvironment();
+    } catch (std::exception &e) {
+        std::cout << e.what() << std::endl;
+        return -1;
+    }
+    const bool lead = job.rank == 0;
+    const bool sliced = in.mapInt.count("slicewires") > 0 || job.world > 1;
+    const int sliceWires = in.mapInt.count("slicewires") ? in.mapInt["slicewires"] : -1;
+    std::ofstream devNull;
+    if (!lead) { devNull.open("/dev/null"); std::cout.rdbuf(devNull.rdbuf()); }
+    auto barrier = [&job]() { if (job.world > 1) { double one = 1.0; job.allreduce(&one, 1); } };
+
     std::cout << "QASM file: " << in.mapString["qasm"] << "\n";
     std::cout << "Meas file: " << in.mapString["measurement"] << "\n";
     std::cout << "Output file: " << in.mapString["outputpath"] << "\n";
-    std::ofstream result(in.mapString["outputpath"]);
+    std::ofstream result(lead ? in.mapString["outputpath"] : std::string("/dev/null"));
     if (!result) {
         std::cout << "Invalid Output File Path" << std::endl;
         return -1;
@@ -65,6 +86,12 @@ int main(int argc, char *argv[]) {
     Timer clock;
     clock.start();
     bool ok = false;
+    // a sliced run walks the plan on the host only (no arithmetic); the device then runs the slices of that plan
+    SlicedContraction::Tensors inputTensors;
+    if (sliced) {
+        for (int i = 0; i < net->GetNumOriginalNodes(); ++i) inputTensors.push_back(net->GetAllNodes()[i]->GetTensorVals());
+        device::Engine::SetPlanOnly(true);
+    }
     try {
         net->ReduceCircuit();
     } catch (std::exception &e) {
@@ -89,7 +116,7 @@ int main(int argc, char *argv[]) {
                 std::cout << "qbbonly=true. Only running qbb on linegraph, not doing contraction.\n";
                 std::cout << "quickbbseconds set to: " << in.mapInt["quickbbseconds"] << std::endl;
                 if (inProcessOrdering) std::cout << "In-process min-fill ordering, width " << lg.runMinFill() << std::endl;
-                else lg.runQuickBB(in.mapInt["quickbbseconds"], &clock, sixtyFour);
+                else if (lead) lg.runQuickBB(in.mapInt["quickbbseconds"], &clock, sixtyFour);
                 std::cout << "QuickBB has been run. Set qbbonly=false and readqbbresonly=true to contract network. Exiting.\n";
                 return 0;
             }
@@ -99,16 +126,38 @@ int main(int argc, char *argv[]) {
                 std::cout << "In-process min-fill ordering, width " << lg.runMinFill() << std::endl;
             } else {
                 std::cout << "quickbbseconds set to: " << in.mapInt["quickbbseconds"] << std::endl;
-                lg.runQuickBB(in.mapInt["quickbbseconds"], &clock, sixtyFour);
+                if (lead) lg.runQuickBB(in.mapInt["quickbbseconds"], &clock, sixtyFour);      // one writer; the others read its file
+                barrier();
             }
             ok = lg.LGContract();
         } catch (std::exception &e) {
             report(e);
         }
-        if (ok) {
+        if (ok && sliced) {
+            device::Engine::SetPlanOnly(false);
+            try {
+                SlicedContraction run(slicing::PlanOfNetwork(*net), sliceWires, job, in.mapInt.count("lanes") ? in.mapInt["lanes"] : 2);
+                const slicing::SlicedPlan &sp = run.Sliced();
+                std::cout << "Index slicing: " << sp.wires.size() << " wire(s) cut, " << sp.NumSlices() << " slices dealt over " << job.world
+                          << " rank(s); " << sp.nInvariant << " of " << sp.plan.steps.size() << " steps are slice-invariant and run once; peak rank of a slice "
+                          << sp.peakRank << "; units per slice " << static_cast<double>(sp.unitsPerSlice) << std::endl;
+                const std::complex<double> value = run.Contract(inputTensors);
+                std::cout << "Result of Contraction" << (onlyContract ? " (also printed to file)" : "") << ": " << value << std::endl;
+                result << "Result of Contraction: " << value << std::endl;
+                if (const char *full = std::getenv("QTORCH_PRINT_FULL")) {
+                    if (std::atoi(full)) { std::cout.precision(17); std::cout << "@@value " << value.real() << " " << value.imag() << std::endl; std::cout.precision(6); }
+                }
+            } catch (std::exception &e) {
+                report(e);
+                ok = false;
+            }
+        } else if (ok) {
             std::cout << "Result of Contraction" << (onlyContract ? " (also printed to file)" : "") << ": " << net->GetFinalValue() << std::endl;
             result << "Result of Contraction: " << net->GetFinalValue() << std::endl;
         }
+    } else if (sliced) {
+        std::cout << "Index slicing / multi-GPU runs need a line-graph contraction method.\n";
+        return -1;
     } else if (method == "simple-stoch" || method == "user-defined") {
         const bool haveSeq = method == "user-defined" && in.mapString.count("user-contract-seq");
         if (method == "user-defined" && !haveSeq)

@@ -898,12 +898,8 @@ int qtb_read_scalar(qtb_ctx *ctx, qtb_tensor t, double out[2]) {
     return QTB_OK;
 }
 
-int qtb_read_scalar_begin(qtb_ctx *ctx, qtb_tensor t, qtb_scalar_read **out) {
-    if (!ctx || !t || !out) return fail(QTB_ERR_INVALID, "null argument");
-    *out = nullptr;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (!t->hasData || !t->d) return fail(QTB_ERR_EMPTY_INPUT, "tensor has no data");
-    ST(flush_locked(ctx));
+// queue a 16-byte device->host copy of *src on the ctx stream into a recycled pinned slot; the slot's event marks its arrival
+static int scalar_read_enqueue(qtb_ctx *ctx, const double2 *src, qtb_scalar_read **out) {
     qtb_scalar_read *r = nullptr;
     if (!ctx->freeReads.empty()) { r = ctx->freeReads.back(); ctx->freeReads.pop_back(); }
     else {
@@ -915,12 +911,21 @@ int qtb_read_scalar_begin(qtb_ctx *ctx, qtb_tensor t, qtb_scalar_read **out) {
             return fail(QTB_ERR_OOM, "scalar read slot allocation failed");
         }
     }
-    cudaError_t e = cudaMemcpyAsync(r->pinned, t->d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(r->pinned, src, 16, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecord(r->done, ctx->stream);
     if (e != cudaSuccess) { ctx->freeReads.push_back(r); return fail(QTB_ERR_CUDA, cudaGetErrorString(e)); }
     ctx->stats.bytes_d2h += 16;
     *out = r;
     return QTB_OK;
+}
+
+int qtb_read_scalar_begin(qtb_ctx *ctx, qtb_tensor t, qtb_scalar_read **out) {
+    if (!ctx || !t || !out) return fail(QTB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!t->hasData || !t->d) return fail(QTB_ERR_EMPTY_INPUT, "tensor has no data");
+    ST(flush_locked(ctx));
+    return scalar_read_enqueue(ctx, t->d, out);
 }
 
 int qtb_read_scalar_end(qtb_ctx *ctx, qtb_scalar_read *r, double out[2]) {
@@ -1116,6 +1121,19 @@ int qtb_allreduce_sum(qtb_ctx *ctx, double *host, int nComplex) {
     return QTB_OK;
 }
 
+// the same reduction on a buffer that already lives on the device: one in-stream ncclAllReduce, no host staging, no wait
+int qtb_allreduce_sum_device(qtb_ctx *ctx, void *dev, int nComplex) {
+    if (!ctx || !dev || nComplex < 0) return fail(QTB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->comm) return fail(QTB_ERR_NCCL, "communicator not initialised (qtb_comm_init)");
+    ST(ensure_device(ctx));
+    ST(flush_locked(ctx));
+    int r = g_nccl.AllReduce(dev, dev, (size_t)nComplex * 2, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+    if (r != 0) return fail(QTB_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    return QTB_OK;
+}
+
 }  // extern "C"
 
 #include "plan.inl"
+#include "sliced.inl"

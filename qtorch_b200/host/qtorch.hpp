@@ -11,4 +11,5 @@
 #include "ContractionTools.h"
 #include "leviParser.hpp"
 #include "preprocess.h"
+#include "Slicing.h"
 using namespace qtorch;

@@ -23,6 +23,13 @@ class _QthPlan(ctypes.Structure):
                 ("steps", ctypes.POINTER(PlanStep)), ("flops", ctypes.c_longlong)]
 
 
+class _QthSlicedPlan(ctypes.Structure):
+    _fields_ = [("nInputs", ctypes.c_int), ("nSteps", ctypes.c_int), ("nInvariant", ctypes.c_int), ("nWires", ctypes.c_int),
+                ("peakRank", ctypes.c_int), ("nCuts", ctypes.c_int), ("inputRanks", ctypes.POINTER(ctypes.c_int)),
+                ("steps", ctypes.POINTER(PlanStep)), ("wires", ctypes.POINTER(ctypes.c_int)), ("cuts", ctypes.POINTER(ctypes.c_int)),
+                ("unitsPerSlice", ctypes.c_double), ("unitsInvariant", ctypes.c_double)]
+
+
 def host_library():
     global _hlib
     if _hlib is None:
@@ -40,6 +47,15 @@ def host_library():
         H.qth_linegraph_end.argtypes = [ctypes.c_void_p, cd, cll, ci]
         H.qth_contract_sequence.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci, ctypes.c_int, cd, cll, ci, cd]
         H.qth_export_plan_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_QthPlan)]
+        H.qth_slice_plan.argtypes = [ctypes.c_int, ci, ctypes.c_int, ctypes.POINTER(PlanStep), ctypes.c_int, ctypes.POINTER(_QthSlicedPlan)]
+        H.qth_slice_tensor.argtypes = [ctypes.c_void_p, ctypes.c_int, ci, ci, ctypes.c_int, ctypes.c_void_p]
+        H.qth_sliced_create.restype = ctypes.c_void_p
+        H.qth_sliced_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 5
+        H.qth_sliced_destroy.argtypes = [ctypes.c_void_p]
+        H.qth_sliced_info.argtypes = [ctypes.c_void_p, cll, cd, cd, cll]
+        H.qth_sliced_stage.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        H.qth_sliced_begin.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        H.qth_sliced_end.argtypes = [ctypes.c_void_p, ctypes.c_int, cd]
         H.qth_maxcut_circuit_text.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, cd, ctypes.c_char_p, ctypes.c_int, ci, ci]
         H.qth_maxcut_final_string.argtypes = [ctypes.c_char_p, ctypes.c_int, cd, ctypes.c_char_p, ci, ctypes.c_int, ctypes.c_uint, cd]
         H.qth_qaoa_create.restype = ctypes.c_void_p
@@ -206,3 +222,91 @@ def export_plan_linegraph(qasm, measure, ordering, reduce=True):
         s = p.steps[i]
         steps.append((s.a, s.b, [s.pos_a[j] for j in range(s.k)], [s.pos_b[j] for j in range(s.k)]))
     return ranks, steps, inputs, p.flops
+
+
+# ---- index slicing: the C++ host's planner and the sliced-amplitude executor (host/Slicing.h) ---------------------------
+
+def _plan_steps(steps):
+    arr = (PlanStep * max(len(steps), 1))()
+    for i, (a, b, pa, pb) in enumerate(steps):
+        arr[i].a, arr[i].b, arr[i].k = a, b, len(pa)
+        for j, (x, y) in enumerate(zip(pa, pb)):
+            arr[i].pos_a[j], arr[i].pos_b[j] = x, y
+    return arr
+
+
+def slice_plan(input_ranks, steps, n_wires):
+    """host only: the C++ planner's choice of wires and its hoisted sliced plan.  Returns a dict with wires as
+    (input tensor, leg) labels, ranks / steps of one slice, n_invariant, cuts {tensor: [(leg, wire), ...]}, units."""
+    H = host_library()
+    out = _QthSlicedPlan()
+    ranks = (ctypes.c_int * max(len(input_ranks), 1))(*input_ranks)
+    rc = H.qth_slice_plan(len(input_ranks), ranks, len(steps), _plan_steps(steps), n_wires, ctypes.byref(out))
+    if rc != 0:
+        _raise(H, rc)
+    label = lambda w: (w // 32, w % 32)
+    cuts = {}
+    for i in range(out.nCuts):
+        cuts.setdefault(out.cuts[3 * i], []).append((out.cuts[3 * i + 1], label(out.cuts[3 * i + 2])))
+    st = []
+    for i in range(out.nSteps):
+        s = out.steps[i]
+        st.append((s.a, s.b, [s.pos_a[j] for j in range(s.k)], [s.pos_b[j] for j in range(s.k)]))
+    return {"wires": [label(out.wires[i]) for i in range(out.nWires)], "ranks": [out.inputRanks[i] for i in range(out.nInputs)],
+            "steps": st, "n_invariant": out.nInvariant, "cuts": cuts, "peak_rank": out.peakRank,
+            "units_per_slice": out.unitsPerSlice, "units_invariant": out.unitsInvariant}
+
+
+def slice_tensor(full, rank, legs, digits):
+    H = host_library()
+    full = np.ascontiguousarray(full, dtype=np.complex128).ravel()
+    out = np.empty(4 ** (rank - len(legs)), dtype=np.complex128)
+    la, da = (ctypes.c_int * max(len(legs), 1))(*legs), (ctypes.c_int * max(len(legs), 1))(*digits)
+    if H.qth_slice_tensor(full.ctypes.data, rank, la, da, len(legs), out.ctypes.data) != 0:
+        _raise(H, 1)
+    return out
+
+
+class SlicedNetwork:
+    """A line-graph network cut into 4^s slices dealt round-robin over the ranks of the job (SlicedContraction in
+    host/Slicing.h): plan once on the host, then per amplitude stage -> begin -> end with no host synchronisation inside,
+    slot scalars summed on the device and ONE in-stream ncclAllReduce.  ordering "" = in-process min-fill.
+    With world > 1 the NCCL communicator must already be initialised on host_api.engine()."""
+
+    def __init__(self, qasm, measure, ordering, reduce=True, slice_wires=-1, lanes=2, rank=0, world=1):
+        self.H = host_library()
+        self.h = self.H.qth_sliced_create(qasm.encode(), measure.encode(), (ordering or "").encode(), 1 if reduce else 0, slice_wires, lanes, rank, world)
+        if not self.h:
+            _raise(self.H, 1)
+        info = (ctypes.c_longlong * 8)()
+        ups, uinv, fl = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        self.H.qth_sliced_info(self.h, info, ctypes.byref(ups), ctypes.byref(uinv), ctypes.byref(fl))
+        (self.slices, self.owned, self.invariant_steps, self.steps, self.peak_rank, self.cut_wires, self.launches_per_slice,
+         self.launches_prefix) = (int(x) for x in info)
+        self.units_per_slice, self.units_invariant, self.units_unsliced = ups.value, uinv.value, fl.value
+        self.units_total = self.units_invariant + (self.units_per_slice - self.units_invariant) * self.slices
+
+    def stage(self, bank=0):
+        if self.H.qth_sliced_stage(self.h, bank) != 0:
+            _raise(self.H, 1)
+
+    def begin(self, bank=0):
+        t = self.H.qth_sliced_begin(self.h, bank)
+        if t < 0:
+            _raise(self.H, 1)
+        return t
+
+    def end(self, ticket):
+        v = (ctypes.c_double * 2)()
+        if self.H.qth_sliced_end(self.h, ticket, v) != 0:
+            _raise(self.H, 1)
+        return complex(v[0], v[1])
+
+    def amplitude(self):
+        self.stage(0)
+        return self.end(self.begin(0))
+
+    def close(self):
+        if self.h:
+            self.H.qth_sliced_destroy(self.h)
+            self.h = None

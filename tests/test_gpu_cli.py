@@ -109,3 +109,57 @@ def test_maxcut_cli_two_ranks_reach_the_single_rank_optimum(built, tmp_path):
     assert abs(best_of(outs[0]) - best_of(r.stdout)) <= 1e-9
     assert open(os.path.join(duo, "angles.txt")).read().split() == open(os.path.join(solo, "angles.txt")).read().split()
     assert not os.path.exists(idfile)
+
+
+def _full_value(stdout):
+    line = [l for l in stdout.splitlines() if l.startswith("@@value")][0].split()
+    return complex(float(line[1]), float(line[2]))
+
+
+def test_qtorch_cli_sliced_small(built, tmp_path):
+    """`>int slicewires 2` on qft8: 16 slices on one rank, same result file text as the unsliced run"""
+    work = _workdir(tmp_path, "qft8_X8.qbb.out")
+    env = dict(os.environ, QTORCH_PRINT_FULL="1")
+    plain = subprocess.run([qt.CLI_PATH, _script(work, "plain", "Samples/qft8.qasm", "Samples/measureSampleOne.txt")], cwd=work,
+                           capture_output=True, text=True, timeout=300, env=env)
+    cut = subprocess.run([qt.CLI_PATH, _script(work, "cut", "Samples/qft8.qasm", "Samples/measureSampleOne.txt", extra=">int slicewires 2\n>int lanes 2\n")],
+                         cwd=work, capture_output=True, text=True, timeout=300, env=env)
+    assert plain.returncode == 0 and cut.returncode == 0, (plain.stdout[-500:], cut.stdout[-800:])
+    assert "16 slices dealt over 1 rank(s)" in cut.stdout
+    assert abs(_full_value(cut.stdout) - 0.030967309712430089) <= 1e-10
+    a, b = _result_lines(os.path.join(work, "plain.out")), _result_lines(os.path.join(work, "cut.out"))
+    assert a[1] == b[1]                                  # the unsliced plan's unit count is reported either way
+    assert a[0].split(",")[0] == b[0].split(",")[0]      # same real part to the 6 printed digits
+
+
+def test_qtorch_cli_sliced_config2_term(built, tmp_path):
+    """the config-2 term <Z27 Z29> through the `qtorch` binary in 16 slices (one rank here; see the two-rank test)"""
+    import json
+    rec = json.load(open(os.path.join(GOLDEN, "networks.json")))["qaoa30_z27z29"]
+    work = _workdir(tmp_path, "qaoa30_z27z29.qbb.out")
+    r = subprocess.run([qt.CLI_PATH, _script(work, "z", "Samples/4regRand30Node5-p1.qasm", "Samples/meas_qaoa30_z27z29.txt", extra=">int slicewires 2\n")],
+                       cwd=work, capture_output=True, text=True, timeout=600, env=dict(os.environ, QTORCH_PRINT_FULL="1"))
+    assert r.returncode == 0, r.stdout[-1000:]
+    assert "16 slices dealt over 1 rank(s)" in r.stdout and "peak rank of a slice 12" in r.stdout
+    assert abs(_full_value(r.stdout) - complex(*rec["value"])) <= 1e-10
+    assert "Number of floating point ops in full contraction: %d" % rec["flops"] in open(os.path.join(work, "z.out")).read()
+
+
+def test_qtorch_cli_sliced_two_ranks(built, tmp_path):
+    """one `qtorch` process per GPU (RANK / WORLD_SIZE / LOCAL_RANK): slices dealt round-robin, one NCCL allreduce, rank 0
+    alone writes the result"""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (NCCL refuses two ranks on one device)")
+    rec = json.load(open(os.path.join(GOLDEN, "networks.json")))["qaoa30_z27z29"]
+    work = _workdir(tmp_path, "qaoa30_z27z29.qbb.out")
+    script = _script(work, "z2", "Samples/4regRand30Node5-p1.qasm", "Samples/meas_qaoa30_z27z29.txt", extra=">int slicewires 2\n")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env.update(QTORCH_PRINT_FULL="1", QTORCH_NCCL_ID_FILE=os.path.join(work, "nccl.id"))
+    procs = [subprocess.Popen([qt.CLI_PATH, script], cwd=work, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              env=dict(env, RANK=str(k), WORLD_SIZE="2", LOCAL_RANK=str(k))) for k in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "16 slices dealt over 2 rank(s)" in outs[0] and outs[1].strip() == ""
+    assert abs(_full_value(outs[0]) - complex(*rec["value"])) <= 1e-10
