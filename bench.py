@@ -1,20 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- QAOA <Z_i Z_j> terms/s on B200 (BASELINE.json metric), workload = BASELINE config 2.
+"""bench.py -- QAOA <Z_i Z_j> terms/s and sliced amplitudes/s on B200 (BASELINE.json metric).
 
-Workload (named in config.workload): p=1 QAOA MaxCut expectation terms of Samples/4regRand30Node5-p1.qasm
-(30 qubits, 4-regular, 60 edges), line-graph ordering frozen in tests/golden/orderings/qaoa30_z27z29.qbb.out
-(one ordering serves every term: the measurement caps do not change the line graph).  One "step" = one full
-term contraction per rank: 299 pairwise steps, 6.935e10 units (5.5e11 flop), four rank-14 DMMA steps + one
-268M-term inner product.  Terms are dealt round-robin to ranks (term = step*N + rank mod 60), no data-path
-collective; the per-step scalars are summed with one NCCL allreduce at the end ("scaling": "weak").
+Headline workload (config.workload) = BASELINE config 2: p=1 QAOA MaxCut expectation terms of
+Samples/4regRand30Node5-p1.qasm (30 qubits, 4-regular, 60 edges), line-graph ordering frozen in
+tests/golden/orderings/qaoa30_z27z29.qbb.out (one ordering serves every term: the measurement caps do not change the
+line graph).  One "step" = one full term contraction per rank: 299 pairwise steps, 6.935e10 units (5.5e11 flop), four
+rank-14 DMMA steps + one 268M-term inner product.  Terms are dealt round-robin to ranks (term = step*N + rank mod 60),
+no data-path collective ("scaling": "weak").
 
   value : device-resident: the compiled plan (qtb_plan_*) with every term's inputs staged in HBM beforehand
   e2e   : the user's call through the C++ host mirror (Network -> ReduceCircuit -> LGContract -> GetFinalValue)
           with .qasm / measurement files in, gate tensors uploaded (H2D) and the scalar read back (D2H) per term
 
---impl reference : the UNMODIFIED reference (oracle/_ref/ref_harness, built from /root/reference/src) replaying the
-same plan on the host cores, each step a bounded sample of the term (plan steps 0..294, all but the four rank-14
-steps and the final inner product), extrapolated by units to terms/s.
+Further keys of the same line (the other halves of the metric, all through the C++14 host):
+  sliced  : BASELINE config 4 -- ONE amplitude of the connected rand-42 circuit (tests/golden/generated/rand42_cn4_d20.qasm,
+            frozen QuickBB plan, 8.67e10 units) index-sliced over the ranks (host/Slicing.h + qtb_sliced_*): strong scaling,
+            slot scalars summed on the device, one in-stream NCCL allreduce per amplitude, two amplitudes in flight;
+            `e2e` re-stages the slices' input tensors from host memory for every amplitude
+  sliced_cfg2 : the same executor on the config-2 term <Z27 Z29> (continuity with round 1)
+  maxcut  : BASELINE config 3 -- the per-edge loop of maxcutQAOA's objective on Samples/3regRand30Node50.dgf, p = 1 and 2,
+            edges dealt over the ranks, one CUDA graph and one in-stream allreduce per objective evaluation
+
+--impl reference : the UNMODIFIED reference (oracle/_ref/ref_harness, built from /root/reference/src, -O2, all host
+threads) on a bounded sample of the headline workload per step: the term's plan replayed up to its four rank-14 steps
+(295 of 299 steps, all measured), plus one step of the large-tensor class (6,13,k=3 -> 13, 4.29e9 units, 1 GB operands) whose per-unit
+rate is applied to the 6.9e10 units of the rank-14 steps and the closing inner product.
 """
 import argparse
 import json
@@ -30,11 +40,48 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 QASM = os.path.join(GOLDEN, "Samples", "4regRand30Node5-p1.qasm")
 ORDERING = os.path.join(GOLDEN, "orderings", "qaoa30_z27z29.qbb.out")
 NETS = os.path.join(GOLDEN, "networks.json")
+MAXCUT = os.path.join(GOLDEN, "maxcut.json")
 N_QUBITS = 30
 UNITS_PER_TERM = 69351174176          # getNumFloatOps() of one term (reference Network.h:884-885), golden
-FP64_PEAK_TFLOPS = 37.1               # measured on this pool's B200: DMMA m8n8k4 probe, profiles/r01_probe_fp64.jsonl
 METRIC = "qaoa_zz_terms_per_s"
 WORKLOAD = "cfg2: 4regRand30Node5-p1.qasm (30q, 4-regular) <ZiZj> terms, frozen linegraph-qbb plan, 299 steps, 6.935e10 units/term"
+CONFIG = {"workload": WORKLOAD, "units_per_term": UNITS_PER_TERM, "l2": "inputs larger than L2 (rank-14 tensors, 4.29 GB each)"}
+CFG4 = "rand42_cn4_d20_zeros"
+BIG_STEP_SAMPLE = (6, 13, 3, [0, 2, 4], [1, 6, 11])     # rA, rB, k, posA, posB: the (6,14,k=3 -> 14) class one rank down (1 GB tensors)
+
+
+def fp64_peak():
+    """(TFLOP/s, where it comes from): MEASURED_PEAKS.json if it carries an FP64 entry, else the DMMA m8n8k4 issue peak
+    measured on this pool's B200 with tools/probe_fp64.cu (profiles/r01_probe_fp64.jsonl, tracked)."""
+    try:
+        m = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        for k in ("fp64_tflops", "fp64_dmma_tflops", "dmma_tflops"):
+            if k in m:
+                return float(m[k]), "MEASURED_PEAKS.json:%s" % k
+    except Exception:
+        pass
+    best = 0.0
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r01_probe_fp64.jsonl")):
+            r = json.loads(line)
+            if r.get("probe") == "dmma_m8n8k4":
+                best = max(best, float(r["tflops"]))
+    except Exception:
+        pass
+    if best > 0:
+        return best, "measured: tools/probe_fp64 DMMA m8n8k4 on this pool's B200 (profiles/r01_probe_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry"
+    return 37.1, "fallback constant (profiles/r01_probe_fp64.jsonl unreadable)"
+
+
+def ncu_traffic():
+    """dram bytes (read + write) of one rank-14 tile-kernel launch from the tracked ncu summary, or None"""
+    for name in ("r02_ncu_gett.json", "r01_ncu_gett.json"):
+        try:
+            r = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return float(r["dram_bytes_read"]) + float(r["dram_bytes_write"]), "profiles/" + name
+        except Exception:
+            continue
+    return None, None
 
 
 def edges_of_circuit():
@@ -107,23 +154,65 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(samples)}
 
 
-def cpu_reference_sample(threads, budget_units=3.0e8):
-    """Time the unmodified reference on the box's host cores over a bounded sample of the term (see module doc).
-    Returns dict(value=terms/s extrapolated by units, seconds, units, steps)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# the CPU arm: the unmodified reference on the box's host cores, bounded sample of the headline term
+def plan_step_table():
+    """(rC, units) of every step of the term's plan, from the host mirror's plan export (host only, no device)"""
+    from qtorch_b200 import host_api
+    rec = json.load(open(NETS))["qaoa30_z27z29"]
+    ranks, steps, _, flops = host_api.export_plan_linegraph(QASM, os.path.join(GOLDEN, rec["measure"]), ORDERING, True)
+    assert flops == UNITS_PER_TERM
+    rk, out = list(ranks), []
+    for a, b, pa, pb in steps:
+        rc = rk[a] + rk[b] - 2 * len(pa)
+        rk.append(rc)
+        out.append((rc, 4 ** (rc + len(pa)), max(rk[a], rk[b])))
+    return out
+
+
+def cpu_reference_sample(threads):
+    """One bounded sample of the term on the reference (see the module doc).  Everything up to the rank-14 steps is
+    MEASURED step by step (small single-threaded steps and the threaded rC >= 8 steps separately); the rank-14 steps and
+    the closing inner product are scaled by units from a measured step of the same class.  Returns a dict or None."""
     from oracle import oracle as O
     if not O.ref_available():
         return None
-    nets = json.load(open(NETS))
-    rec = nets["qaoa30_z27z29"]
+    table = plan_step_table()
+    first_big = min(i for i, (rc, u, rin) in enumerate(table) if max(rc, rin) >= 14)
+    measured_units = sum(u for rc, u, _ in table[:first_big])
+    rec = json.load(open(NETS))["qaoa30_z27z29"]
     with tempfile.TemporaryDirectory() as d:
         plan = os.path.join(d, "plan.txt")
         with open(plan, "w") as f:
             for p in rec["plan"]:
                 f.write("%s %s\n" % tuple(p.split(",")))
-        meas = os.path.join(GOLDEN, rec["measure"])
-        out = O.ref_harness(["seq", QASM, meas, plan, threads, budget_units], cwd=GOLDEN, timeout=900)
-    units, secs, steps = int(out["flops"][0]), float(out["seconds"][0]), int(out["steps"][0])
-    return {"value": (units / secs) / UNITS_PER_TERM, "seconds": secs, "units": units, "steps": steps}
+        out = O.ref_harness(["seq", QASM, os.path.join(GOLDEN, rec["measure"]), plan, threads, measured_units], cwd=GOLDEN, timeout=1800)
+    steps = [(int(s[0]), int(s[3]), int(s[4]), float(s[5])) for s in out["step"]]          # index, rC, units, seconds
+    assert len(steps) == first_big and sum(s[2] for s in steps) == measured_units, (len(steps), first_big)
+    small = [s for s in steps if s[1] < 8]                     # reference runs these on one thread (Network.h:941)
+    mid = [s for s in steps if s[1] >= 8]                      # threaded regime, results up to rank 11
+    rA, rB, k, pA, pB = BIG_STEP_SAMPLE
+    big = O.ref_harness(["stepbench", rA, rB, k] + pA + pB + [threads], timeout=1800)
+    big_units, big_secs = int(big["flops"][0]), float(big["seconds"][0])
+    rest_units = UNITS_PER_TERM - measured_units               # four rank-14 steps + the inner product
+    secs_term = sum(s[3] for s in steps) + rest_units * (big_secs / big_units)
+    return {"seconds_per_term": secs_term, "value": 1.0 / secs_term,
+            "sample_seconds": sum(s[3] for s in steps) + big_secs,
+            "small_steps": {"n": len(small), "units": sum(s[2] for s in small), "seconds": sum(s[3] for s in small)},
+            "threaded_steps_rank8to11": {"n": len(mid), "units": sum(s[2] for s in mid), "seconds": sum(s[3] for s in mid)},
+            "large_class_step": {"shape": "(%d,%d,k=%d -> %d)" % (rA, rB, k, rA + rB - 2 * k), "units": big_units, "seconds": big_secs,
+                                 "units_per_s": big_units / big_secs},
+            "extrapolated_units": rest_units}
+
+
+def sample_text(c):
+    return ("unmodified reference (-O2): plan steps 0..%d of 299 replayed and timed (%d single-threaded steps %.3g units %.2f s; %d threaded steps "
+            "rC 8..11 %.3g units %.2f s) + one threaded large-class step %s %.3g units %.2f s = %.3g units/s, applied to the remaining %.3g units "
+            "(four rank-14 steps + inner product)"
+            % (c["small_steps"]["n"] + c["threaded_steps_rank8to11"]["n"] - 1, c["small_steps"]["n"], c["small_steps"]["units"], c["small_steps"]["seconds"],
+               c["threaded_steps_rank8to11"]["n"], c["threaded_steps_rank8to11"]["units"], c["threaded_steps_rank8to11"]["seconds"],
+               c["large_class_step"]["shape"], c["large_class_step"]["units"], c["large_class_step"]["seconds"], c["large_class_step"]["units_per_s"],
+               c["extrapolated_units"]))
 
 
 def run_reference_arm(args):
@@ -133,26 +222,29 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
         cpu_reference_sample(threads)
-    times, last = [], None
+    secs, last = [], None
     for _ in range(args.steps):
         last = cpu_reference_sample(threads)
         if last is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness not built (needs /root/reference at build time)"}))
             return
-        times.append(last["seconds"] * UNITS_PER_TERM / last["units"])       # extrapolated seconds per term
-    sec_per_term = sum(times) / len(times)
+        secs.append(last["seconds_per_term"])
+    sec_per_term = sum(secs) / len(secs)
     value = 1.0 / sec_per_term
-    sample = "plan steps 0..%d of 299 (%.3g of %.3g units) per step, extrapolated by units" % (last["steps"] - 1, last["units"], UNITS_PER_TERM)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "terms/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_per_term * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_build": "g++ -O2 -std=c++11 -pthread, unmodified /root/reference/src via oracle/ref_harness.cpp"},
-        "cpu_baseline": {"value": value, "unit": "terms/s", "cores": threads, "kind": "reference", "sample": sample},
+        "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": "terms/s", "cores": threads, "kind": "reference", "sample": sample_text(last),
+                         "sample_seconds_per_step": last["sample_seconds"], "detail": {k: last[k] for k in ("small_steps", "threaded_steps_rank8to11", "large_class_step")}},
         "e2e": {"value": value, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_build": "g++ -O2 -std=c++11 -pthread, unmodified /root/reference/src via oracle/ref_harness.cpp",
+        "note": "ms_per_step is the reference's time for ONE TERM as named in config (measured part + unit-scaled part); each arm step RUNS only the bounded sample (sample_seconds_per_step)",
     }))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,13 +280,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = host_api.engine()                 # the host mirror's engine context (shared by both measured paths)
+    def max_over_ranks(*vals):
+        if dist is None:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    eng = host_api.engine()                 # the host mirror's engine context (shared by every measured path)
+    if dist is not None:                    # the engine's own NCCL communicator (in-stream scalar reductions)
+        uid = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(world, rank, uid[0])
     edges = edges_of_circuit()
     assert len(edges) == 60
     tmp = tempfile.mkdtemp(prefix="qtb_bench_")
     meas_files = [write_measure_file(tmp, e) for e in edges]
     W, K = args.warmup, args.steps
     my_terms = [(s * world + rank) % len(edges) for s in range(W + K)]
+    nets = json.load(open(NETS))
+    golden_rec = nets["qaoa30_z27z29"]
 
     # ---------------- device-resident path: one compiled plan, per-term input sets staged in HBM ----------------
     ranks, steps, inputs0, flops = host_api.export_plan_linegraph(QASM, meas_files[my_terms[0]], ORDERING, True)
@@ -225,6 +330,8 @@ def main():
     trace = eng.read_trace()
     eng.trace(False)
     values_dev.append(plan.read_output()[0])
+    plan_launches = plan.launches
+    plan.destroy()                                  # give the unsliced plan's 13 GB back
 
     # ---------------- end-to-end path: files in, host mirror, scalar out ----------------------------------------
     values_e2e = []
@@ -244,60 +351,106 @@ def main():
         job = nxt
     ms_e2e = eng.timer_stop()
     barrier()
-    sampler.stop()
     stats_e2e = eng.stats()
 
-    # ---------------- second half of the metric: one amplitude index-sliced over the ranks --------------------------
-    # The <Z27 Z29> term cut into 4^s slices (qtorch_b200/slicing.py: wires chosen greedily; two wires: peak rank 14 -> 12,
-    # total units x1.005); slices dealt round-robin to ranks, one compiled plan, per-slice inputs staged in HBM, the
-    # partial sums meet in one NCCL allreduce per amplitude.  Strong scaling of ONE expectation value.
-    from qtorch_b200 import slicing
-    from qtorch_b200.dispatch import Dispatcher
-    golden_rec = json.load(open(NETS))["qaoa30_z27z29"]
-    g_ranks, g_steps, g_inputs, _ = host_api.export_plan_linegraph(QASM, os.path.join(GOLDEN, golden_rec["measure"]), ORDERING, True)
-    # as few slices as give every rank work: 4 slices (one wire, peak rank 13) up to 4 ranks, 16 slices (two wires, peak
-    # rank 12) for 8 -- bigger slices keep the tile kernel's prologue and tail a smaller share of each step
-    SLICE_WIRES = 1
-    while 4 ** SLICE_WIRES < world:
-        SLICE_WIRES += 1
-    wires = slicing.choose_wires(g_ranks, g_steps, SLICE_WIRES)
-    all_sl = slicing.all_slices(wires)
-    plan_launches = plan.launches
-    plan.destroy()                                  # give the unsliced plan's 13 GB back first
-    # steps no cut wire reaches (270 of the 299 here) are hoisted into a prefix that runs once per amplitude
-    splan, cuts, n_invariant = slicing.compile_sliced(eng, g_ranks, g_steps, wires)
-    disp = Dispatcher(rank, world)
-    owned = disp.owned(len(all_sl))
-    for slot, u in enumerate(owned):
-        splan.stage_inputs(slot, slicing.slice_inputs(g_inputs, g_ranks, cuts, wires, all_sl[u]))
-    if dist is not None:
-        uid = [eng.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init(world, rank, uid[0])
+    # ---------------- sliced amplitudes: one network cut over the ranks (strong scaling) ------------------------------
+    K2 = max(20, K)
 
-    def one_amplitude():
-        part = splan.run_slots(range(len(owned))) if owned else 0.0 + 0.0j      # prefix once, suffix per slice, one sync
-        if dist is not None:
-            part = complex(eng.allreduce_sum(np.array([part], dtype=np.complex128))[0])
-        return part
+    def sliced_run(rec, label):
+        """SlicedContraction (host/Slicing.h): as few cut wires as give every rank a slice, but at least one; slices dealt
+        round-robin; per amplitude: [stage] -> begin -> end, two amplitudes in flight, ONE in-stream allreduce each."""
+        s_wires = 1
+        while 4 ** s_wires < world:
+            s_wires += 1
+        paths = [os.path.join(GOLDEN, rec[k]) for k in ("qasm", "measure", "ordering")]
+        net = host_api.SlicedNetwork(*paths, True, slice_wires=s_wires, lanes=2, rank=rank, world=world)
+        ref = complex(*rec["value"])
+        net.stage(0); net.stage(1)
+        ok = True
+        for _ in range(3):
+            ok = ok and abs(net.end(net.begin(0)) - ref) <= 1e-10 * max(1.0, abs(ref))
+        # inputs resident: the slices' input tensors stay staged in HBM
+        eng.reset_stats()
+        barrier()
+        t0 = time.perf_counter()
+        eng.timer_start()
+        tick = [net.begin(0), net.begin(1)]
+        for i in range(K2):
+            v = net.end(tick[i % 2])
+            ok = ok and abs(v - ref) <= 1e-10 * max(1.0, abs(ref))
+            tick[i % 2] = net.begin(i % 2) if i + 2 < K2 else None
+        ms_res = eng.timer_stop()
+        wall_res = (time.perf_counter() - t0) * 1e3
+        barrier()
+        st_res = eng.stats()
+        # end to end: every amplitude re-stages its slices from host memory (H2D) before it runs
+        eng.reset_stats()
+        barrier()
+        eng.timer_start()
+        net.stage(0); tick = [net.begin(0), None]
+        for i in range(K2):
+            if i + 1 < K2:
+                net.stage((i + 1) % 2)
+                tick[(i + 1) % 2] = net.begin((i + 1) % 2)
+            v = net.end(tick[i % 2])
+            ok = ok and abs(v - ref) <= 1e-10 * max(1.0, abs(ref))
+        ms_e = eng.timer_stop()
+        barrier()
+        st_e = eng.stats()
+        ms_res, ms_e, wall_res = max_over_ranks(ms_res, ms_e, wall_res)
+        out = {"metric": "sliced_amplitudes_per_s", "value": K2 / (ms_res * 1e-3), "unit": "amplitudes/s", "ms_per_amplitude": ms_res / K2,
+               "wall_ms_per_amplitude": wall_res / K2, "amplitudes_timed": K2, "in_flight": 2,
+               "e2e": {"value": K2 / (ms_e * 1e-3), "unit": "amplitudes/s", "ms_per_amplitude": ms_e / K2,
+                       "h2d_bytes_per_amplitude": st_e["bytes_h2d"] // K2, "d2h_bytes_per_amplitude": st_e["bytes_d2h"] // K2},
+               "workload": label + ", cut into 4^%d slices dealt round-robin over %d rank(s), slot sums on the device, one in-stream NCCL allreduce per amplitude" % (net.cut_wires, world),
+               "slices": net.slices, "slices_this_rank": net.owned, "lanes": 2, "invariant_steps_run_once": net.invariant_steps, "steps": net.steps,
+               "peak_rank": net.peak_rank, "units_vs_unsliced": net.units_total / net.units_unsliced, "units_unsliced": net.units_unsliced,
+               "gpu_launches_rank0": int(st_res["launches"]), "matches_reference_1e-10": bool(ok), "scaling": "strong"}
+        net.close()
+        return out
 
-    for _ in range(2):
-        amp = one_amplitude()
-    K2 = 5
-    barrier()
-    eng.timer_start()
-    for _ in range(K2):
-        amp = one_amplitude()
-    ms_sliced = eng.timer_stop()
-    barrier()
-    sliced_ok = abs(amp - complex(*golden_rec["value"])) <= 1e-10
-    sliced_units = splan.prefix_units + (splan.units - splan.prefix_units) * len(all_sl)
-    splan.destroy()
+    sliced4 = sliced_run(nets[CFG4], "cfg4: connected rand-42 circuit (rxyz, cn=4, depth 20, seed 57; generated/rand42_cn4_d20.qasm), amplitude <0..0|rho|0..0>, frozen linegraph-qbb plan 8.67e10 units")
+    sliced2 = sliced_run(golden_rec, "cfg2 term <Z27 Z29> (6.935e10 units)")
+
+    # ---------------- config 3: the per-edge loop of the maxcutQAOA objective ------------------------------------------
+    def maxcut_run(name, evals):
+        rec = json.load(open(MAXCUT))[name]
+        graph, p = os.path.join(GOLDEN, rec["graph"]), rec["p"]
+        n_edges = len(rec["terms"])
+        q = host_api.QaoaObjective(graph, p, rank=rank, world=world)
+        reduce = world > 1
+        fp = q.objective(rec["betas_gammas"], reduce, n_edges)
+        ok = abs(fp - rec["fp"]) <= 1e-10 * max(1.0, abs(rec["fp"])) if (reduce or world == 1) else True
+        vals, _ = q.evaluate(rec["betas_gammas"])
+        ok = ok and all(abs(v - complex(*rec["terms"][e])) <= 1e-10 for e, v in zip(q.owned, vals))
+        for i in range(10):
+            q.objective(rec["betas_gammas"], reduce, n_edges)
+        eng.reset_stats()
+        barrier()
+        eng.timer_start()
+        for i in range(evals):                     # an optimiser's sequence: every evaluation waits for the previous value
+            q.objective([a * (1.0 + 1e-3 * (i % 7)) for a in rec["betas_gammas"]], reduce, n_edges)
+        ms = eng.timer_stop()
+        barrier()
+        st = eng.stats()
+        (ms,) = max_over_ranks(ms)
+        out = {"p": p, "terms_per_s": n_edges * evals / (ms * 1e-3), "evaluations_per_s": evals / (ms * 1e-3), "ms_per_evaluation": ms / evals,
+               "evaluations_timed": evals, "edges": n_edges, "edges_this_rank": len(q.owned), "units_per_evaluation_this_rank": q.units,
+               "kernel_launches_per_evaluation": q.launches, "h2d_bytes_per_evaluation": st["bytes_h2d"] // evals,
+               "d2h_bytes_per_evaluation": st["bytes_d2h"] // evals, "matches_reference_1e-10": bool(ok)}
+        q.close()
+        return out
+
+    maxcut = {"metric": "maxcut_zz_terms_per_s", "unit": "terms/s", "scaling": "strong",
+              "workload": "cfg3: 3regRand30Node50.dgf (30 vertices, 45 edges) objective F_p through QaoaObjective (host/maxcut.h): edges dealt "
+                          "round-robin over %d rank(s), one CUDA graph (2p gate tables H2D, scatter, one CTA per edge, gather) and one in-stream "
+                          "NCCL allreduce per evaluation; evaluations are sequential like the optimiser's" % world,
+              "p1": maxcut_run("3reg30_p1_default", 300), "p2": maxcut_run("3reg30_p2_default", 200)}
+    maxcut["value"] = maxcut["p1"]["terms_per_s"]
 
     # ---------------- beyond the reference's plan: the same term on the in-process min-fill ordering -------------------
     # (LineGraph::runMinFill, SURVEY 8f-3).  NOT the headline: the headline keeps the reference's own QuickBB plan bit
-    # for bit; this shows what dropping the external quickbb_64 call buys (36 ms of ordering instead of 20 s, and a plan
-    # of 2.2e10 instead of 6.9e10 units for this circuit).  Same value within 1e-10.
+    # for bit; this shows what dropping the external quickbb_64 call buys.  Same value within 1e-10.
     m_ranks, m_steps, m_inputs, m_flops = host_api.export_plan_linegraph(QASM, os.path.join(GOLDEN, golden_rec["measure"]), "", True)
     mplan = eng.plan(m_ranks, m_steps)
     mplan.stage_inputs(0, m_inputs)
@@ -311,23 +464,18 @@ def main():
     ms_minfill = eng.timer_stop() / 10
     minfill_ok = abs(mval - complex(*golden_rec["value"])) <= 1e-10
     mplan.destroy()
+    sampler.stop()
 
     # both paths must agree with each other (and with the golden term when it is among them)
     for s in range(W):
         assert abs(values_dev[s] - values_e2e[s]) <= 1e-10 * max(1.0, abs(values_e2e[s])), (s, values_dev[s], values_e2e[s])
-    golden = json.load(open(NETS))["qaoa30_z27z29"]["value"]
     if (29, 27) in edges and my_terms[0] == edges.index((29, 27)):
-        assert abs(values_e2e[0] - complex(*golden)) <= 1e-10
+        assert abs(values_e2e[0] - complex(*golden_rec["value"])) <= 1e-10
 
     # max over ranks of the timed regions; one scalar allreduce of the per-rank partial sums (the term dispatcher's reduction)
     f_p = sum(0.5 * (1.0 - v.real) for v in values_e2e[W:])
+    ms_dev, ms_e2e = max_over_ranks(ms_dev, ms_e2e)
     if dist is not None:
-        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
-        t2 = torch.tensor([ms_sliced], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        ms_sliced = float(t2[0])
         f_p = eng.allreduce_sum(np.array([f_p], dtype=np.complex128))[0].real
     barrier()
 
@@ -335,6 +483,7 @@ def main():
         terms = K * world
         value = terms / (ms_dev * 1e-3)
         e2e = terms / (ms_e2e * 1e-3)
+        peak, peak_src = fp64_peak()
         # roofline of the dominant kernel: the DMMA tile kernel on the rank-14 steps (trace code 2; the fourth rank-14 step
         # runs fused with the closing inner product, code 6, and is left out of this average)
         gett = [r for r in trace if r["kernel"] == 2 and max(r["rank_a"], r["rank_b"]) >= 9 and r["k"] == 3 and r["rank_a"] + r["rank_b"] - 6 == 14]
@@ -346,18 +495,19 @@ def main():
             ach = flop / (avg_ms * 1e-3) / 1e12
             variant = os.environ.get("QTB_GETT_C1", "2")
             three_m = variant in ("2", "3")
+            traffic, traffic_src = ncu_traffic()
             roof = {"bound": "tensor", "kernel": "k_gett (warp-specialised FP64 DMMA tiles, the four rank-14 steps), variant %s (%s complex product)" % (variant, "3M" if three_m else "4M"),
-                    "achieved": ach, "peak": FP64_PEAK_TFLOPS,
-                    "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     # achieved counts the ALGORITHMIC 8 flops per complex MAC; the 3M kernel issues 6 on the tensor pipe
-                    "tensor_pipe_flops_per_unit": 6 if three_m else 8, "tensor_pipe_frac": ach * (0.75 if three_m else 1.0) / FP64_PEAK_TFLOPS,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one (10,10,k=3 -> 14) launch, ncu --set full
-                    # (profiles/r01_ncu_summary.txt: 0.259 GB read + 4.238 GB written); algorithmic 16 * (2 * 4^10 + 4^14) = 4.33e9
-                    "traffic": 4.50e9, "launches_timed": len(gett), "avg_ms": avg_ms,
+                    "tensor_pipe_flops_per_unit": 6 if three_m else 8, "tensor_pipe_frac": ach * (0.75 if three_m else 1.0) / peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one (10,10,k=3 -> 14) launch from the tracked ncu --set full
+                    # summary; algorithmic 16 * (2 * 4^10 + 4^14) = 4.33e9
+                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": 16.0 * (2 * 4 ** 10 + 4 ** 14),
+                    "launches_timed": len(gett), "avg_ms": avg_ms,
                     "share_of_step": sum(r["ms"] for r in gett) / total_ms,
                     # the fourth rank-14 step runs fused with the closing inner product (trace code 6, same tile kernel)
                     "fused_step_share_of_step": sum(r["ms"] for r in trace if r["kernel"] == 6) / total_ms,
-                    "peak_source": "measured: tools/probe_fp64 DMMA m8n8k4 on this pool's B200 (profiles/r01_probe_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry"}
+                    "peak_source": peak_src}
         by_kind = {}
         for r in trace:
             by_kind.setdefault(str(r["kernel"]), [0, 0.0])
@@ -368,24 +518,20 @@ def main():
             threads = os.cpu_count() or 1
             c = cpu_reference_sample(threads)
             if c is not None:
-                cpu = {"value": c["value"], "unit": "terms/s", "cores": threads, "kind": "reference",
-                       "sample": "unmodified reference (-O2) replaying plan steps 0..%d of 299 (%.3g of %.3g units, %.1f s), extrapolated by units"
-                                 % (c["steps"] - 1, c["units"], UNITS_PER_TERM, c["seconds"])}
+                cpu = {"value": c["value"], "unit": "terms/s", "cores": threads, "kind": "reference", "sample": sample_text(c),
+                       "sample_seconds": c["sample_seconds"], "detail": {k: c[k] for k in ("small_steps", "threaded_steps_rank8to11", "large_class_step")}}
         line = {
             "metric": METRIC, "value": value, "unit": "terms/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "terms_per_step": world, "l2": "inputs larger than L2 (rank-14 tensors, 4.29 GB each)",
-                       "plan_launches_per_term": plan_launches, "units_per_term": UNITS_PER_TERM},
+            "config": CONFIG,
             "e2e": {"value": e2e, "unit": "terms/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": stats_e2e["bytes_h2d"] // K, "d2h_bytes_per_step": stats_e2e["bytes_d2h"] // K},
             "gpu_launches": int(stats_dev["launches"]),
             "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
+            "details": {"terms_per_step": world, "plan_launches_per_term": plan_launches},
             "kernel_time_ms_by_kind": {k: {"launches": v[0], "ms": v[1]} for k, v in by_kind.items()},
             "f_p_partial": f_p,
-            "sliced": {"metric": "sliced_amplitudes_per_s", "value": K2 / (ms_sliced * 1e-3), "unit": "amplitudes/s", "ms_per_amplitude": ms_sliced / K2,
-                       "workload": "cfg2 term <Z27 Z29> cut into 4^%d slices dealt round-robin over %d rank(s), one NCCL allreduce per amplitude" % (SLICE_WIRES, world),
-                       "slices": len(all_sl), "invariant_steps_run_once": n_invariant, "peak_rank": slicing.plan_cost(g_ranks, g_steps, frozenset(wires))[1],
-                       "units_vs_unsliced": sliced_units / UNITS_PER_TERM, "matches_reference_1e-10": bool(sliced_ok), "scaling": "strong"},
+            "sliced": sliced4, "sliced_cfg2": sliced2, "maxcut": maxcut,
             "minfill_plan": {"note": "same term on the in-process min-fill ordering instead of the reference's QuickBB plan (not the headline)",
                              "terms_per_s_per_gpu": 1e3 / ms_minfill, "ms_per_term": ms_minfill, "units_per_term": m_flops,
                              "matches_reference_1e-10": bool(minfill_ok)},

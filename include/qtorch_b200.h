@@ -161,6 +161,25 @@ int qtb_sliced_launches(qtb_sliced *sliced, int *prefix_launches);   /* kernel l
  * ONE launch (one CTA per plan), the n scalars come back with one synchronisation.
  * host_inputs[i] is plan i's array of input pointers; host_out receives n (re, im) pairs.                       */
 int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const double *const *const *host_inputs, double *host_out);
+/* Term batches: n independent scalar plans whose inputs stay resident in HBM and of which only a few small gate tensors
+ * change between evaluations -- the QAOA objective (maxcut.cpp:162-204: same per-edge networks, 2p angles per call).
+ * qtb_batch_set_inputs uploads a plan's inputs once; qtb_batch_bind declares that input `input` of plan `plan` is table
+ * `table` of the per-evaluation table set (n_tables tensors of rank table_rank, e.g. Rz(-gamma_l) and Rx(2 beta_l)).
+ * One evaluation = one CUDA-graph launch: H2D of the tables (n_tables * 16 * 4^table_rank bytes), scatter into the bound
+ * inputs, all plans (one CTA per plan when they are grouped micro-steps only, forked streams otherwise), gather of the n
+ * scalars and their sum in a fixed order, optionally ONE in-stream ncclAllReduce of the sum (replaces f_pVal += ...,
+ * maxcut.cpp:196), one D2H.  begin returns at once; end waits and returns the sum (over all ranks after an allreduce) and,
+ * if `terms` is not NULL, this rank's n individual (re, im) pairs.                                                      */
+typedef struct qtb_batch_s qtb_batch;
+int qtb_batch_create(qtb_ctx *ctx, qtb_plan *const *plans, int n, int n_tables, int table_rank, qtb_batch **out);
+int qtb_batch_destroy(qtb_ctx *ctx, qtb_batch *batch);
+int qtb_batch_set_inputs(qtb_ctx *ctx, qtb_batch *batch, int plan, const double *const *host_inputs);
+int qtb_batch_bind(qtb_ctx *ctx, qtb_batch *batch, int plan, int input, int table);
+int qtb_batch_begin(qtb_ctx *ctx, qtb_batch *batch, const double *tables_re_im, int allreduce);
+int qtb_batch_end(qtb_ctx *ctx, qtb_batch *batch, double sum_re_im[2], double *terms_re_im);
+int qtb_batch_run(qtb_ctx *ctx, qtb_batch *batch, const double *tables_re_im, int allreduce, double sum_re_im[2], double *terms_re_im);
+int qtb_batch_launches(qtb_batch *batch);          /* kernel launches inside one evaluation */
+long long qtb_batch_units(qtb_batch *batch);
 /* sum_steps 4^(rC+k): the reference's getNumFloatOps() contribution of this plan (Network.h:884-885). */
 long long qtb_plan_units(qtb_plan *plan);
 /* Number of kernel launches one qtb_plan_run_device enqueues. */
@@ -196,9 +215,9 @@ typedef struct qtb_step_trace {
                                             7 streaming kernel (big tensor x tensor of <= 64 elements)                    */
     float ms;
 } qtb_step_trace;
-/* Largest step (4^n complex multiply-adds, n = 0..8) that may ride in a grouped micro-step launch.  A micro-step runs
+/* Largest step (4^n complex multiply-adds, n = 0..10) that may ride in a grouped micro-step launch.  A micro-step runs
  * on one SM, so the limit trades launch count against single-SM load bandwidth: default 6; callers that evaluate many
- * independent plans side by side (qtb_plans_run_batched) raise it to 8 before creating their plans.                 */
+ * independent plans side by side (qtb_plans_run_batched, qtb_batch_*) raise it (up to 10) before creating their plans.                 */
 int qtb_ctx_set_micro_limit(qtb_ctx *ctx, int log4_units);
 int qtb_ctx_get_micro_limit(qtb_ctx *ctx);
 /* CUDA-event stopwatch on the ctx stream (bench.py times the hot path with it): start flushes deferred work

@@ -15,6 +15,8 @@
 // Modes
 //   step  rA rB k pA.. pB.. A.bin B.bin C.bin      one pairwise contraction through
 //                                                   Network::ContractNodes (src/Network.h:715)
+//   stepbench rA rB k pA.. pB.. threads            the same single step on seeded pseudo-random tensors built in memory, timed
+//                                                   (the CPU arm's sample of the "large tensor" step class; nothing written)
 //   gate  NAME [angle|file]                         dump a gate/measurement tensor table (src/Node.h:197-898)
 //   lg    qasm measure qbb.out reduce threads       ReduceCircuit + LineGraph::LGContract on a frozen ordering
 //   qbb   qasm measure seconds cnf out stats reduce run quickbb_64 (must be on PATH) -> ordering files
@@ -118,6 +120,47 @@ static int mode_step(int argc, char **argv) {
     fwrite(C->GetTensorVals().data(), sizeof(cplx), C->GetTensorVals().size(), f);
     fclose(f);
     printf("@@rank %d\n@@flops %lld\n", C->mRank, net.getNumFloatOps());
+    return 0;
+}
+
+// one step of a given shape on in-memory pseudo-random operands through Network::ContractNodes, timed
+static int mode_stepbench(int argc, char **argv) {
+    int a = 2;
+    int rA = atoi(argv[a++]), rB = atoi(argv[a++]), k = atoi(argv[a++]);
+    std::vector<int> pA(k), pB(k);
+    for (int i = 0; i < k; i++) pA[i] = atoi(argv[a++]);
+    for (int i = 0; i < k; i++) pB[i] = atoi(argv[a++]);
+    const int threads = atoi(argv[a++]);
+    auto A = std::make_shared<Node>(rA);
+    auto B = std::make_shared<Node>(rB);
+    unsigned long long x = 88172645463325252ull;          // xorshift64: cheap, deterministic filler
+    auto fill = [&x](std::vector<cplx> &v) {
+        for (auto &e : v) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            const double re = (double)(x & 0xfffff) / 1048576.0 - 0.5;
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            e = cplx(re, (double)(x & 0xfffff) / 1048576.0 - 0.5);
+        }
+    };
+    fill(A->GetTensorVals());
+    fill(B->GetTensorVals());
+    std::vector<std::shared_ptr<Wire>> wa(rA), wb(rB);
+    for (int i = 0; i < k; i++) {
+        auto w = std::make_shared<Wire>(A, B, 0);
+        wa[pA[i]] = w; wb[pB[i]] = w;
+    }
+    for (int i = 0; i < rA; i++) if (!wa[i]) wa[i] = std::make_shared<Wire>(A, nullptr, 0);
+    for (int i = 0; i < rB; i++) if (!wb[i]) wb[i] = std::make_shared<Wire>(nullptr, B, 0);
+    for (auto &w : wa) A->GetWires().push_back(w);
+    for (auto &w : wb) B->GetWires().push_back(w);
+    Network net;
+    net.SetNumThreads(threads);
+    const double t0 = now_s();
+    std::shared_ptr<Node> C = net.ContractNodes(A, B, 1000);
+    const double dt = now_s() - t0;
+    if (!C) { printf("@@rejected\n"); return 0; }
+    printf("@@rank %d\n@@flops %lld\n@@seconds %.6f\n", C->mRank, net.getNumFloatOps(), dt);
+    print_value("probe", C->GetTensorVals()[C->GetTensorVals().size() / 3]);
     return 0;
 }
 
@@ -299,6 +342,7 @@ int main(int argc, char **argv) {
     std::string m = argv[1];
     try {
         if (m == "step") return mode_step(argc, argv);
+        if (m == "stepbench") return mode_stepbench(argc, argv);
         if (m == "gate") return mode_gate(argc, argv);
         if (m == "lg") return mode_lg(argc, argv);
         if (m == "qbb") return mode_qbb(argc, argv);

@@ -26,7 +26,9 @@ ABI_SYMBOLS = [
     "qtb_tensor_upload", "qtb_tensor_download", "qtb_read_scalar", "qtb_read_scalar_begin", "qtb_read_scalar_end", "qtb_contract",
     "qtb_plan_create", "qtb_plan_destroy", "qtb_plan_run_host", "qtb_plan_upload_inputs",
     "qtb_plan_run_device", "qtb_plan_read_output", "qtb_plan_stage_inputs", "qtb_plan_run_device_slot", "qtb_plan_create_sliced", "qtb_plan_run_slots", "qtb_plan_prefix_units", "qtb_plans_run_batched", "qtb_plan_output_rank", "qtb_plan_units", "qtb_plan_launches",
-    "qtb_comm_unique_id", "qtb_comm_init", "qtb_comm_destroy", "qtb_allreduce_sum",
+    "qtb_sliced_create", "qtb_sliced_destroy", "qtb_sliced_stage", "qtb_sliced_begin", "qtb_sliced_lanes", "qtb_sliced_units", "qtb_sliced_prefix_units", "qtb_sliced_launches",
+    "qtb_batch_create", "qtb_batch_destroy", "qtb_batch_set_inputs", "qtb_batch_bind", "qtb_batch_begin", "qtb_batch_end", "qtb_batch_run", "qtb_batch_launches", "qtb_batch_units",
+    "qtb_comm_unique_id", "qtb_comm_init", "qtb_comm_destroy", "qtb_allreduce_sum", "qtb_allreduce_sum_device",
     "qtb_ctx_stats", "qtb_ctx_reset_stats", "qtb_ctx_timer_start", "qtb_ctx_timer_stop", "qtb_ctx_set_micro_limit", "qtb_ctx_get_micro_limit", "qtb_ctx_trace_enable", "qtb_ctx_trace_read",
 ]
 

@@ -256,9 +256,10 @@ void *qth_sliced_create(const char *qasm, const char *measure, const char *qbbOu
     }
     device::Engine::SetPlanOnly(before);
     try {
+        // world < 0: this process takes rank's share of a |world|-rank job but skips the reduction (profiling one rank's load)
         device::Job job;
-        job.rank = rank; job.world = world;
-        h->run.reset(new SlicedContraction(plan, nSliceWires, job, lanes));
+        job.rank = rank; job.world = world < 0 ? -world : world;
+        h->run.reset(new SlicedContraction(plan, nSliceWires, job, lanes, world > 0));
     } catch (std::exception &e) { g_err = e.what(); delete h; return nullptr; }
     return h;
 }
@@ -315,6 +316,19 @@ int qth_qaoa_evaluate(void *h, const double *betasGammas, int n, double *termsRe
             fp += 0.5 * (1.0 - vals[i].real());
         }
         if (partialFp) *partialFp = fp;
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// F_p for the angles through QaoaObjective's own path: one graph launch; with reduce != 0 the sum over ranks is ONE
+// in-stream ncclAllReduce (the communicator must be initialised on qth_engine_ctx()) and every rank gets the full F_p
+int qth_qaoa_objective(void *h, const double *betasGammas, int n, int reduce, int numEdgesTotal, double *fp) {
+    try {
+        QaoaObjective *q = static_cast<QaoaObjective *>(h);
+        std::vector<double> bg(betasGammas, betasGammas + n);
+        q->Begin(bg, reduce != 0);
+        const std::complex<double> sum = q->End();
+        const double nEdges = reduce ? static_cast<double>(numEdgesTotal) : static_cast<double>(q->OwnedEdges().size());
+        *fp = 0.5 * (nEdges - sum.real());
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }

@@ -43,7 +43,7 @@ static int fail(int status, const std::string &msg) { g_lastError = msg; return 
 // kernel families
 // A micro-step runs on ONE SM inside the grouped launch, so its size limit trades launch count against the
 // load bandwidth of a single SM (2 x 16 B per complex MAC): 4^6 MACs by default for latency-bound single plans,
-// raised to 4^8 by callers that run many plans side by side (qtb_ctx_set_micro_limit; the QAOA term dispatcher).
+// raised to 4^8..4^10 by callers that run many plans side by side (qtb_ctx_set_micro_limit; the QAOA term dispatcher).
 static const int MICRO_DEFAULT_LOG4 = 6;
 static const int MICRO_MAX_RANK = 7;
 
@@ -743,7 +743,7 @@ static int ctx_init(qtb_ctx *ctx, int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(QTB_ERR_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only");
     ctx->numSMs = prop.multiProcessorCount;
-    if (const char *e = getenv("QTB_MICRO_LOG4")) ctx->microLog4 = std::max(0, std::min(8, atoi(e)));
+    if (const char *e = getenv("QTB_MICRO_LOG4")) ctx->microLog4 = std::max(0, std::min(10, atoi(e)));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaMallocHost((void **)&ctx->ringHost, ctx->ringSize));
     CU(cudaMalloc((void **)&ctx->ringDev, ctx->ringSize));
@@ -1042,7 +1042,7 @@ int qtb_ctx_timer_stop(qtb_ctx *ctx, float *ms) {
     return QTB_OK;
 }
 int qtb_ctx_set_micro_limit(qtb_ctx *ctx, int log4Units) {
-    if (!ctx || log4Units < 0 || log4Units > 8) return fail(QTB_ERR_INVALID, "micro limit must be 0..8 (4^n complex MACs)");
+    if (!ctx || log4Units < 0 || log4Units > 10) return fail(QTB_ERR_INVALID, "micro limit must be 0..10 (4^n complex MACs)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ST(flush_locked(ctx));
     ctx->microLog4 = log4Units;
@@ -1137,3 +1137,4 @@ int qtb_allreduce_sum_device(qtb_ctx *ctx, void *dev, int nComplex) {
 
 #include "plan.inl"
 #include "sliced.inl"
+#include "batch.inl"

@@ -36,6 +36,11 @@ struct qtb_plan_s {
     // slots, so qtb_plan_run_slots runs them once and only segs[prefixSegs..) per slot; their results stay live.
     int nPrefixSteps = 0; size_t prefixSegs = 0; int launchesPrefix = 0; long long prefixUnits = 0;
     cudaGraphExec_t graphPrefix = nullptr, graphSuffix = nullptr; bool partGraphsTried = false;
+    // result buffers in allocation order, split at the prefix / suffix boundary: another replica of the same plan can be
+    // compiled onto the SAME addresses for either phase (the sliced executor shares prefix results between lanes and
+    // suffix scratch between the two amplitudes a lane has in flight)
+    std::vector<void *> prefixAllocs, suffixAllocs;
+    bool prefixOnly = false;
 };
 
 static bool plan_graphs_enabled() {
@@ -43,6 +48,9 @@ static bool plan_graphs_enabled() {
     if (v < 0) { const char *e = getenv("QTB_PLAN_GRAPH"); v = (e && !atoi(e)) ? 0 : 1; }
     return v == 1;
 }
+
+static int plan_create_replica(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps, const qtb_plan_step *steps, int nPrefix,
+                               const qtb_plan *prefixDonor, const qtb_plan *suffixDonor, bool prefixOnly, qtb_plan **out);
 
 static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s, size_t segBegin = 0, size_t segEnd = (size_t)-1) {
     if (segEnd > pl->segs.size()) segEnd = pl->segs.size();
@@ -80,6 +88,15 @@ int qtb_plan_create(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps
 }
 
 int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps, const qtb_plan_step *steps, int nPrefix, qtb_plan **out) {
+    return plan_create_replica(ctx, nInputs, inputRanks, nSteps, steps, nPrefix, nullptr, nullptr, false, out);
+}
+
+}  // extern "C"
+
+// prefixDonor / suffixDonor: replicas of the same plan whose result buffers this one re-uses for that phase (same
+// allocation order => same tensor-to-buffer map).  prefixOnly: compile the invariant prefix alone.
+static int plan_create_replica(qtb_ctx *ctx, int nInputs, const int *inputRanks, int nSteps, const qtb_plan_step *steps, int nPrefix,
+                               const qtb_plan *prefixDonor, const qtb_plan *suffixDonor, bool prefixOnly, qtb_plan **out) {
     if (!ctx || !out || nInputs < 0 || nSteps < 1 || (nInputs > 0 && !inputRanks) || !steps) return fail(QTB_ERR_INVALID, "bad plan arguments");
     if (nPrefix < 0 || nPrefix > nSteps) return fail(QTB_ERR_INVALID, "bad invariant-prefix length");
     if (nPrefix == nSteps) nPrefix = 0;              // nothing varies: an ordinary plan
@@ -147,15 +164,42 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int
         deferred.clear();
     };
     pl->nPrefixSteps = nPrefix;
+    pl->prefixOnly = prefixOnly;
+    if (prefixOnly && nPrefix < 1) return bail(fail(QTB_ERR_INVALID, "a prefix-only replica needs an invariant prefix"));
     // a tensor made by the invariant prefix (or a plan input) must survive every slot's pass over the suffix
     auto releasable = [&](int t, int atStep) { return t >= nInputs && !(atStep >= nPrefix && t < nInputs + nPrefix); };
-    for (int i = 0; i < nSteps; i++) {
+    // result buffers: from this plan's pool, or -- phase by phase -- the addresses a donor replica got for the same request
+    std::vector<char> borrowed(nT, 0);                   // tensor lives in a donor's buffer: never released into OUR pool
+    size_t replayPre = 0, replaySuf = 0;
+    auto allocResult = [&](int step, int rk, int tensorId, void **outp) -> int {
+        const bool inPrefix = step < nPrefix;
+        const qtb_plan *donor = inPrefix ? prefixDonor : suffixDonor;
+        if (donor) {
+            const std::vector<void *> &rec = inPrefix ? donor->prefixAllocs : donor->suffixAllocs;
+            size_t &cur = inPrefix ? replayPre : replaySuf;
+            if (cur >= rec.size()) return fail(QTB_ERR_INVALID, "donor replica does not match this plan");
+            *outp = rec[cur++];
+            if (tensorId >= 0) borrowed[tensorId] = 1;
+        } else {
+            ST(pl->pool.alloc(rk, outp));
+        }
+        (inPrefix ? pl->prefixAllocs : pl->suffixAllocs).push_back(*outp);
+        return QTB_OK;
+    };
+    auto releaseTensor = [&](int t, void *ptr) { if (!borrowed[t]) pl->pool.release(rank[t], ptr); };
+    const int nCompiled = prefixOnly ? nPrefix : nSteps;
+    for (int i = 0; i < nCompiled; i++) {
         const qtb_plan_step &s = steps[i];
         const StepGeom &g = geoms[i];
         GettChoice gc{0, false};
         const int kind = choose_kind(g, gc, ctx->microLog4);
         pl->units += (long long)g.units();
-        if (nPrefix > 0 && i == nPrefix) { closeMicro(); pl->prefixSegs = pl->segs.size(); pl->prefixUnits = pl->units - (long long)g.units(); }
+        if (nPrefix > 0 && i == nPrefix) {
+            closeMicro(); pl->prefixSegs = pl->segs.size(); pl->prefixUnits = pl->units - (long long)g.units();
+            // suffix results never land in memory the prefix phase has used: the prefix of the NEXT amplitude may already be
+            // running (on its own copy of the prefix buffers) while this amplitude's slices are still being contracted
+            for (auto &fl : pl->pool.freeList) fl.clear();
+        }
         // fusion: this DMMA step followed by the inner product of its result with another tensor
         if (i + 1 < nSteps && i + 1 != nPrefix && (steps[i + 1].a == nInputs + i || steps[i + 1].b == nInputs + i)) {
             const bool tIsA = steps[i + 1].a == nInputs + i;
@@ -163,7 +207,7 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int
             if (choose_kind(geoms[i + 1], gc2, ctx->microLog4) == KIND_REDUCE && fusable_pair(g, kind, gc, geoms[i + 1], tIsA)) {
                 closeMicro();
                 void *outp = nullptr;
-                { int st = pl->pool.alloc(0, &outp); if (st != QTB_OK) return bail(st); }
+                { int st = allocResult(i + 1, 0, nInputs + i + 1, &outp); if (st != QTB_OK) return bail(st); }
                 const int dId = tIsA ? steps[i + 1].b : steps[i + 1].a;
                 PlanSeg sg; sg.micro = false; sg.fused = true; sg.g = g; sg.kind = KIND_GETT; sg.gc = gc; sg.nSteps = 2;
                 sg.A = dev[s.a]; sg.B = dev[s.b]; sg.C = (double2 *)outp; sg.g2 = geoms[i + 1]; sg.tIsA = tIsA; sg.D = dev[dId];
@@ -171,15 +215,15 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int
                 dev[nInputs + i] = nullptr;                       // the intermediate is never materialised
                 dev[nInputs + i + 1] = (double2 *)outp;
                 pl->units += (long long)geoms[i + 1].units();
-                if (releasable(s.a, i)) pl->pool.release(rank[s.a], dev[s.a]);
-                if (releasable(s.b, i)) pl->pool.release(rank[s.b], dev[s.b]);
-                if (releasable(dId, i)) pl->pool.release(rank[dId], dev[dId]);
+                if (releasable(s.a, i)) releaseTensor(s.a, dev[s.a]);
+                if (releasable(s.b, i)) releaseTensor(s.b, dev[s.b]);
+                if (releasable(dId, i)) releaseTensor(dId, dev[dId]);
                 ++i;                                              // the inner-product step is consumed
                 continue;
             }
         }
         void *cp = nullptr;
-        { int st = pl->pool.alloc(g.rC, &cp); if (st != QTB_OK) return bail(st); }
+        { int st = allocResult(i, g.rC, nInputs + i, &cp); if (st != QTB_OK) return bail(st); }
         dev[nInputs + i] = (double2 *)cp;
         if (kind == KIND_MICRO) {
             PendingStep ps;
@@ -188,20 +232,21 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int
             cur.push_back(ps);
             levelOf[nInputs + i] = ps.level + 1;
             pl->nMicroSteps++;
-            if (releasable(s.a, i)) deferred.push_back({rank[s.a], (void *)dev[s.a]});
-            if (releasable(s.b, i)) deferred.push_back({rank[s.b], (void *)dev[s.b]});
+            if (releasable(s.a, i) && !borrowed[s.a]) deferred.push_back({rank[s.a], (void *)dev[s.a]});
+            if (releasable(s.b, i) && !borrowed[s.b]) deferred.push_back({rank[s.b], (void *)dev[s.b]});
         } else {
             closeMicro();
             PlanSeg sg; sg.micro = false; sg.g = g; sg.kind = kind; sg.gc = gc; sg.nSteps = 1;
             sg.A = dev[s.a]; sg.B = dev[s.b]; sg.C = dev[nInputs + i];
             pl->segs.push_back(sg);
-            if (releasable(s.a, i)) pl->pool.release(rank[s.a], dev[s.a]);
-            if (releasable(s.b, i)) pl->pool.release(rank[s.b], dev[s.b]);
+            if (releasable(s.a, i)) releaseTensor(s.a, dev[s.a]);
+            if (releasable(s.b, i)) releaseTensor(s.b, dev[s.b]);
         }
     }
     closeMicro();
-    pl->nSteps = nSteps;
-    pl->outDev = dev[nT - 1]; pl->outRank = rank[nT - 1];
+    if (prefixOnly) { pl->prefixSegs = pl->segs.size(); pl->prefixUnits = pl->units; }
+    pl->nSteps = nCompiled;
+    pl->outDev = prefixOnly ? nullptr : dev[nT - 1]; pl->outRank = rank[nT - 1];
     pl->launches = 0;
     for (size_t si = 0; si < pl->segs.size(); si++) {
         const PlanSeg &sg = pl->segs[si];
@@ -238,6 +283,8 @@ int qtb_plan_create_sliced(qtb_ctx *ctx, int nInputs, const int *inputRanks, int
     *out = pl;
     return QTB_OK;
 }
+
+extern "C" {
 
 int qtb_plan_destroy(qtb_ctx *ctx, qtb_plan *pl) {
     if (!pl) return QTB_OK;

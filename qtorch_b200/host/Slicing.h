@@ -284,8 +284,8 @@ public:
     typedef std::vector<std::vector<std::complex<double>>> Tensors;
 
     // nSliceWires < 0: as few wires as give every rank a slice.  lanes: plan replicas per rank (see qtb_sliced_create).
-    SlicedContraction(const slicing::Plan &plan, int nSliceWires, const device::Job &job, int lanes = 2)
-        : mFullRanks(plan.inputRanks), mRank(job.rank), mWorld(job.world), mReduce(job.world > 1) {
+    SlicedContraction(const slicing::Plan &plan, int nSliceWires, const device::Job &job, int lanes = 2, bool reduceOverRanks = true)
+        : mFullRanks(plan.inputRanks), mRank(job.rank), mWorld(job.world), mReduce(reduceOverRanks && job.world > 1) {
         if (nSliceWires < 0) { nSliceWires = 0; while ((1 << (2 * nSliceWires)) < job.world) ++nSliceWires; }
         mSliced = slicing::SlicePlan(plan, slicing::ChooseWires(plan, nSliceWires));
         for (size_t u = static_cast<size_t>(mRank); u < mSliced.NumSlices(); u += static_cast<size_t>(mWorld)) mOwned.push_back(u);

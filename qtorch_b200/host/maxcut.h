@@ -6,8 +6,9 @@
 // New: QaoaObjective -- every edge's light-cone circuit is built IN MEMORY (no input/tempMaxCut.qasm round trip;
 // angles still pass through the 6-significant-digit text form and std::stof, so tensors are bit-identical to what
 // the reference parses back), planned once (plan topology does not depend on the angles), compiled to a device
-// plan, and all edges owned by this rank are evaluated in one grouped launch per objective evaluation
-// (qtb_plans_run_batched).  Edges are dealt round-robin over ranks; the partial sums meet in one allreduce.
+// plan, and all edges owned by this rank are evaluated as ONE CUDA-graph launch per objective evaluation (qtb_batch_*:
+// only the 2p gate tables travel to the device, the plans' other inputs stay resident).  Edges are dealt round-robin over
+// ranks; the sum meets in one in-stream NCCL allreduce.
 #pragma once
 
 #include <fstream>
@@ -139,29 +140,45 @@ inline void applyU_CsThenU_Bs(const std::vector<std::pair<int, int>> &objectiveF
 class QaoaObjective {
 public:
     // rank/world: which share of the edges this process owns (edge e belongs to rank e % world).
-    // allreduce: sums an array of n doubles in place over all ranks (nullptr for a single rank).
+    // allreduce: non-null when the process belongs to a multi-rank job (device::Job::FromEnvironment has joined the NCCL
+    // communicator on the engine context): operator() then sums the objective over all ranks with ONE in-stream
+    // ncclAllReduce per evaluation.  The functor itself is only used by callers that reduce on the host.
     QaoaObjective(const ExtraData &data, int rank = 0, int world = 1, std::function<void(double *, int)> allreduce = nullptr,
                   int planTries = 8)
         : mData(data), mRank(rank), mWorld(world), mAllReduce(allreduce) {
         for (size_t e = static_cast<size_t>(rank); e < mData.pairs.size(); e += static_cast<size_t>(world)) mOwned.push_back(static_cast<int>(e));
         std::vector<double> bg(2 * mData.p);
         for (int i = 0; i < mData.p; ++i) { bg[i] = 0.392699; bg[i + mData.p] = 0.785399; }      // maxcut.cpp:155-157
-        // many small plans evaluated side by side (one CTA each): let larger steps ride in the grouped launch
+        // many small plans evaluated side by side (one CTA each): let larger steps ride in the grouped launch, so that a
+        // whole evaluation is ONE launch of grouped micro-steps between the table scatter and the gather
         qtb_ctx *ctx = device::Engine::Get().ctx();
         const int before = qtb_ctx_get_micro_limit(ctx);
-        device::check(qtb_ctx_set_micro_limit(ctx, 8));
+        device::check(qtb_ctx_set_micro_limit(ctx, 10));
         try {
             for (int e : mOwned) mTerms.push_back(BuildTerm(e, bg, planTries));
         } catch (...) {
             qtb_ctx_set_micro_limit(ctx, before);
+            DestroyPlans();
             throw;
         }
         device::check(qtb_ctx_set_micro_limit(ctx, before));
+        if (mTerms.empty()) return;
+        // the batch: plans resident, table l = Rz(-gamma_l), table p + l = Rx(2 beta_l)
+        std::vector<qtb_plan *> plans;
+        for (auto &t : mTerms) plans.push_back(t.plan);
+        try {
+            device::check(qtb_batch_create(ctx, plans.data(), static_cast<int>(plans.size()), 2 * mData.p, 2, &mBatch));
+            for (size_t i = 0; i < mTerms.size(); ++i) {
+                device::check(qtb_batch_set_inputs(ctx, mBatch, static_cast<int>(i), mTerms[i].ptrs.data()));
+                for (const auto &sl : mTerms[i].slots)
+                    device::check(qtb_batch_bind(ctx, mBatch, static_cast<int>(i), sl.input, sl.isRx ? mData.p + sl.layer : sl.layer));
+            }
+        } catch (...) {
+            DestroyPlans();
+            throw;
+        }
     }
-    ~QaoaObjective() {
-        if (device::Engine::Get().alive())
-            for (auto &t : mTerms) if (t.plan) qtb_plan_destroy(device::Engine::Get().ctx(), t.plan);
-    }
+    ~QaoaObjective() { DestroyPlans(); }
     QaoaObjective(const QaoaObjective &) = delete;
     QaoaObjective &operator=(const QaoaObjective &) = delete;
 
@@ -180,40 +197,45 @@ public:
         return m;
     }
 
-    // <Z Z> of every edge owned by this rank, one grouped launch
-    std::vector<std::complex<double>> EvaluateOwnedTerms(const std::vector<double> &betas_gammas) {
-        std::vector<qtb_plan *> plans;
-        std::vector<const double *const *> inputPtrs;
-        for (auto &t : mTerms) {
-            RefreshAngles(t, betas_gammas);
-            plans.push_back(t.plan);
-            inputPtrs.push_back(t.ptrs.data());
-        }
-        std::vector<double> out(2 * mTerms.size());
+    // start one evaluation: 2p gate tables up, one graph launch, [one in-stream allreduce of the sum], results queued
+    void Begin(const std::vector<double> &betas_gammas, bool reduceOverRanks) {
+        if (mTerms.empty() && !(reduceOverRanks && mWorld > 1)) return;
+        if (mTerms.empty()) throw InvalidFunctionInput();             // a rank without edges cannot join the reduction (more ranks than edges)
+        const std::vector<std::complex<double>> tables = GateTables(betas_gammas);
+        device::check(qtb_batch_begin(device::Engine::Get().ctx(), mBatch, reinterpret_cast<const double *>(tables.data()), reduceOverRanks && mWorld > 1 ? 1 : 0));
+    }
+    // wait for it: sum of <Z Z> over this rank's edges (over all edges of all ranks after a reduction); `terms`, if given,
+    // receives this rank's individual values
+    std::complex<double> End(std::vector<std::complex<double>> *terms = nullptr) {
+        double sum[2] = {0.0, 0.0};
+        if (terms) terms->assign(mTerms.size(), std::complex<double>(0.0));
         if (!mTerms.empty())
-            device::check(qtb_plans_run_batched(device::Engine::Get().ctx(), plans.data(), static_cast<int>(plans.size()), inputPtrs.data(), out.data()));
-        std::vector<std::complex<double>> vals(mTerms.size());
-        for (size_t i = 0; i < mTerms.size(); ++i) vals[i] = {out[2 * i], out[2 * i + 1]};
+            device::check(qtb_batch_end(device::Engine::Get().ctx(), mBatch, sum, terms ? reinterpret_cast<double *>(terms->data()) : nullptr));
+        return {sum[0], sum[1]};
+    }
+
+    // <Z Z> of every edge owned by this rank, one graph launch
+    std::vector<std::complex<double>> EvaluateOwnedTerms(const std::vector<double> &betas_gammas) {
+        std::vector<std::complex<double>> vals;
+        Begin(betas_gammas, false);
+        End(&vals);
         return vals;
     }
 
     // F_p = sum_edges 1/2 (1 - Re<Z Z>)   (maxcut.cpp:196), summed over ranks
     double operator()(const std::vector<double> &betas_gammas) {
-        double partial = 0.0;
-        for (const auto &v : EvaluateOwnedTerms(betas_gammas)) partial += 0.5 * (1.0 - v.real());
-        if (mAllReduce && mWorld > 1) {
-            double buf[2] = {partial, 0.0};
-            mAllReduce(buf, 1);
-            partial = buf[0];
-        }
+        const bool reduce = mAllReduce && mWorld > 1;
+        Begin(betas_gammas, reduce);
+        const std::complex<double> sum = End();
         ++mEvaluations;
-        return partial;
+        const double nEdges = reduce ? static_cast<double>(mData.pairs.size()) : static_cast<double>(mOwned.size());
+        return 0.5 * (nEdges - sum.real());
     }
 
     const std::vector<int> &OwnedEdges() const { return mOwned; }
     long long Evaluations() const { return mEvaluations; }
     long long UnitsPerEvaluation() const { long long u = 0; for (const auto &t : mTerms) u += t.units; return u; }
-    int LaunchesPerEvaluation() const { int n = 0; bool allMicro = true; for (const auto &t : mTerms) { n += qtb_plan_launches(t.plan); if (qtb_plan_launches(t.plan) != 1) allMicro = false; } return allMicro ? 1 : n; }
+    int LaunchesPerEvaluation() const { return mBatch ? qtb_batch_launches(mBatch) : 0; }
 
 private:
     struct AngleSlot { int input; bool isRx; int layer; };     // which plan input is Rz(-gamma_layer) / Rx(2 beta_layer)
@@ -226,6 +248,13 @@ private:
         std::vector<AngleSlot> slots;
     };
 
+    void DestroyPlans() {
+        if (!device::Engine::Get().alive()) return;
+        qtb_ctx *ctx = device::Engine::Get().ctx();
+        if (mBatch) { qtb_batch_destroy(ctx, mBatch); mBatch = nullptr; }
+        for (auto &t : mTerms) if (t.plan) { qtb_plan_destroy(ctx, t.plan); t.plan = nullptr; }
+    }
+
     // the value the reference's parser would obtain: default-precision text, then std::stof (Network.h:342,402)
     static double ThroughText(double angle) {
         std::ostringstream os;
@@ -233,24 +262,52 @@ private:
         return static_cast<double>(std::stof(os.str()));
     }
 
+    // the 2p gate tensors of one evaluation, built by the same constructors the parser uses: [Rz(-gamma_l)]_l, [Rx(2 beta_l)]_l
+    std::vector<std::complex<double>> GateTables(const std::vector<double> &bg) const {
+        std::vector<std::complex<double>> tables;
+        for (int l = 0; l < mData.p; ++l) {
+            RzNode g(ThroughText(-bg[l + mData.p]));
+            tables.insert(tables.end(), g.GetTensorVals().begin(), g.GetTensorVals().end());
+        }
+        for (int l = 0; l < mData.p; ++l) {
+            RxNode g(ThroughText(bg[l] * 2.0));
+            tables.insert(tables.end(), g.GetTensorVals().begin(), g.GetTensorVals().end());
+        }
+        return tables;
+    }
+
     Term BuildTerm(int edge, const std::vector<double> &bg, int planTries) {
         Term t;
         t.edge = edge;
         const int nq = mData.qubitsNeeded[edge];
         const std::string text = CircuitText(edge, bg), meas = MeasurementText(nq);
-        // plan search on the host only (plan-only mode records steps without arithmetic): best of a few seeded
-        // stochastic searches, cheapest by the reference's own unit count
+        // plan search on the host only (plan-only mode records steps without arithmetic): a few seeded stochastic searches
+        // (the reference's own planner for this path, maxcut.cpp:189-190) and the in-process min-fill line-graph order;
+        // cheapest by the reference's own unit count.  The plan does not depend on the angles.
         const bool before = device::Engine::PlanOnly();
         device::Engine::SetPlanOnly(true);
         std::shared_ptr<Network> best;
-        for (int attempt = 0; attempt < planTries; ++attempt) {
-            std::istringstream qs(text);
-            std::shared_ptr<Network> net = std::make_shared<Network>(qs, meas);
-            if (attempt == 0) SnapshotInputs(*net, t);
-            ContractionTools tools(net);
-            tools.SetSeed(1000003u * static_cast<unsigned>(edge) + static_cast<unsigned>(attempt));
-            tools.Contract(Stochastic);
-            if (!best || net->getNumFloatOps() < best->getNumFloatOps()) best = net;
+        try {
+            for (int attempt = 0; attempt <= planTries; ++attempt) {
+                std::istringstream qs(text);
+                std::shared_ptr<Network> net = std::make_shared<Network>(qs, meas);
+                if (attempt == 0) SnapshotInputs(*net, t);
+                if (attempt < planTries) {
+                    ContractionTools tools(net);
+                    tools.SetSeed(1000003u * static_cast<unsigned>(edge) + static_cast<unsigned>(attempt));
+                    tools.Contract(Stochastic);
+                } else {
+                    net->ReduceCircuit();
+                    LineGraph lg(net);
+                    lg.SetQBBOutFiles("/dev/null", "", "/dev/null");
+                    lg.runMinFill();
+                    lg.LGContract();
+                }
+                if (!best || net->getNumFloatOps() < best->getNumFloatOps()) best = net;
+            }
+        } catch (...) {
+            device::Engine::SetPlanOnly(before);
+            throw;
         }
         device::Engine::SetPlanOnly(before);
         t.units = best->getNumFloatOps();
@@ -274,7 +331,6 @@ private:
     // edge one Rz, then one Rx per qubit)
     void SnapshotInputs(Network &net, Term &t) {
         const int n = net.GetNumOriginalNodes();
-        std::vector<int> rzSeen(mData.p, 0), rxSeen(mData.p, 0);
         const int rzPerLayer = static_cast<int>(mData.realIterations[t.edge].size()), rxPerLayer = mData.qubitsNeeded[t.edge];
         int rzCount = 0, rxCount = 0;
         for (int i = 0; i < n; ++i) {
@@ -283,20 +339,6 @@ private:
             if (node->GetTypeOfNode() == GateType::RZ) t.slots.push_back({i, false, rzCount++ / rzPerLayer});
             else if (node->GetTypeOfNode() == GateType::RX) t.slots.push_back({i, true, rxCount++ / rxPerLayer});
         }
-        (void)rzSeen; (void)rxSeen;
-    }
-
-    void RefreshAngles(Term &t, const std::vector<double> &bg) {
-        for (const auto &s : t.slots) {
-            if (s.isRx) {
-                RxNode g(ThroughText(bg[s.layer] * 2.0));
-                t.inputs[s.input] = g.GetTensorVals();
-            } else {
-                RzNode g(ThroughText(-bg[s.layer + mData.p]));
-                t.inputs[s.input] = g.GetTensorVals();
-            }
-            t.ptrs[s.input] = reinterpret_cast<const double *>(t.inputs[s.input].data());
-        }
     }
 
     ExtraData mData;
@@ -304,6 +346,7 @@ private:
     std::function<void(double *, int)> mAllReduce;
     std::vector<int> mOwned;
     std::vector<Term> mTerms;
+    qtb_batch *mBatch{nullptr};
     long long mEvaluations{0};
 };
 

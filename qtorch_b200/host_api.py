@@ -67,6 +67,7 @@ def host_library():
         H.qth_qaoa_units.argtypes = [ctypes.c_void_p]
         H.qth_qaoa_launches.argtypes = [ctypes.c_void_p]
         H.qth_qaoa_evaluate.argtypes = [ctypes.c_void_p, cd, ctypes.c_int, cd, cd]
+        H.qth_qaoa_objective.argtypes = [ctypes.c_void_p, cd, ctypes.c_int, ctypes.c_int, ctypes.c_int, cd]
         H.qth_qaoa_circuit_text.argtypes = [ctypes.c_void_p, ctypes.c_int, cd, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
         _hlib = H
     return _hlib
@@ -123,6 +124,15 @@ class QaoaObjective:
             _raise(self.H, rc)
         vals = np.array([complex(out[2 * i], out[2 * i + 1]) for i in range(len(self.owned))])
         return vals, fp.value
+
+    def objective(self, betas_gammas, reduce=False, n_edges_total=0):
+        """F_p for the angles: one graph launch; reduce=True adds ONE in-stream NCCL allreduce over the job's ranks"""
+        bg = (ctypes.c_double * len(betas_gammas))(*betas_gammas)
+        fp = ctypes.c_double()
+        rc = self.H.qth_qaoa_objective(self.h, bg, len(betas_gammas), 1 if reduce else 0, n_edges_total, ctypes.byref(fp))
+        if rc != 0:
+            _raise(self.H, rc)
+        return fp.value
 
     def circuit_text(self, edge, betas_gammas):
         bg = (ctypes.c_double * len(betas_gammas))(*betas_gammas)

@@ -13,14 +13,15 @@ from qtorch_b200 import host_api
 G = os.path.join(ROOT, "tests", "golden")
 nets = json.load(open(os.path.join(G, "networks.json")))
 eng = host_api.engine()
-which = sys.argv[1:] or ["qaoa30_z27z29", "rand42_cn4_d20_zeros"]
+which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["qaoa30_z27z29", "rand42_cn4_d20_zeros"]
+SHARES = [(1, 0, 2), (1, 0, 4), (2, 0, 8), (2, 3, 8)] if "--shares" in sys.argv else [(0, 0, 1), (1, 0, 1), (2, 0, 1), (1, 0, 2), (1, 0, 4), (2, 0, 8), (2, 3, 8)]
 for name in which:
     rec = nets[name]
     paths = [os.path.join(G, rec[k]) for k in ("qasm", "measure", "ordering")]
     ref = complex(*rec["value"])
-    for s, rank, world in [(0, 0, 1), (1, 0, 1), (2, 0, 1), (1, 0, 2), (1, 0, 4), (2, 0, 8), (2, 3, 8)]:
+    for s, rank, world in SHARES:
         for lanes in (1, 2, 3):
-            net = host_api.SlicedNetwork(*paths, True, slice_wires=s, lanes=lanes, rank=rank, world=1 if world == 1 else world)
+            net = host_api.SlicedNetwork(*paths, True, slice_wires=s, lanes=lanes, rank=rank, world=1 if world == 1 else -world)
             # world > 1 here only selects this rank's share of the slices (no communicator: the reduction is skipped below)
             net.stage(0); net.stage(1)
             try:
