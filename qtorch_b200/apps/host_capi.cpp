@@ -49,6 +49,27 @@ int qth_contract_linegraph(const char *qasm, const char *measure, const char *qb
     }
 }
 
+// The same value through the plan cache (host/PlanCache.h): the first call for a (qasm, ordering, reduce) triple does the
+// host bookkeeping once and compiles the plan; every later call only swaps the measurement caps and replays the graph.
+int qth_contract_cached(const char *qasm, const char *measure, const char *qbbOut, int reduce, double value[2], long long *flops, int *nodes,
+                        int *cacheHit) {
+    try {
+        PlanCache &cache = PlanCache::Get();
+        const long long hitsBefore = cache.Hits();
+        std::shared_ptr<CompiledCircuit> c = cache.Lookup(qasm, qbbOut ? qbbOut : "", reduce != 0);
+        if (cacheHit) *cacheHit = cache.Hits() > hitsBefore ? 1 : 0;
+        const std::complex<double> v = c->EvaluateFile(measure);
+        value[0] = v.real(); value[1] = v.imag();
+        if (flops) *flops = c->Units();
+        if (nodes) *nodes = c->NumNodes();
+        return c->Ok() ? 0 : 2;
+    } catch (std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+void qth_plan_cache_clear(void) { PlanCache::Get().Clear(); }
+
 // The same call split in two, so that a caller with many networks (the 60 <ZiZj> terms of one QAOA evaluation) can
 // overlap the host bookkeeping of network i+1 with the device work of network i: `begin` parses, reduces, walks the
 // ordering and enqueues every step (no synchronisation -- Network::GetFinalValue is lazy); `end` reads the scalar back.

@@ -5,6 +5,9 @@
 // the lg.cnf / qbb.out / qbb-stats.out files (default output/), and for the line-graph methods
 //   ">int slicewires N"  index-slice the network over N wires (4^N slices; host/Slicing.h), -1 = as few as give every
 //                        rank a slice;   ">int lanes N"  plan replicas per GPU (default 2).
+//   ">string measurementlist FILE"  every line of FILE names a measurement file; the circuit is reduced, ordered and
+//                        compiled ONCE (host/PlanCache.h) and each measurement is evaluated by swapping the rank-1 caps
+//                        and replaying the compiled plan (one result line per measurement).
 // Multi-GPU: start one process per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment (e.g.
 // `torchrun --no-python --nproc-per-node 8 qtorch script.inp`): the slices are dealt round-robin over the ranks, the
 // partial sums meet in one NCCL allreduce, rank 0 alone prints and writes the result file.  With WORLD_SIZE > 1 and no
@@ -132,6 +135,25 @@ int main(int argc, char *argv[]) {
             ok = lg.LGContract();
         } catch (std::exception &e) {
             report(e);
+        }
+        if (ok && !sliced && in.mapString.count("measurementlist")) {
+            // the same circuit under many measurements: compile once, replay per measurement (the walk above fixed the
+            // ordering file; its own result is reported first, as usual)
+            try {
+                std::shared_ptr<CompiledCircuit> cc = PlanCache::Get().Lookup(in.mapString["qasm"], lg.QBBOutFile(), true);
+                std::ifstream list(in.mapString["measurementlist"]);
+                std::string mfile;
+                while (std::getline(list, mfile)) {
+                    if (mfile.empty()) continue;
+                    const std::complex<double> v = cc->EvaluateFile(mfile);
+                    std::cout << "Result of Contraction [" << mfile << "]: " << v << std::endl;
+                    result << "Result of Contraction [" << mfile << "]: " << v << std::endl;
+                }
+                std::cout << "Compiled plan: " << cc->Launches() << " kernel launch(es) per measurement, " << cc->Evaluations() << " measurements evaluated" << std::endl;
+            } catch (std::exception &e) {
+                report(e);
+                ok = false;
+            }
         }
         if (ok && sliced) {
             device::Engine::SetPlanOnly(false);

@@ -8,7 +8,9 @@
 // shared memory and is read as a broadcast.  Consecutive threads read consecutive elements of X for every s and write
 // consecutive elements of C for every y; when the small operand's legs come first in C (C index = y + N x) the block's
 // 256 N outputs form one contiguous run and are transposed through shared memory so that the stores stream as well.
-// No tile staging, no tensor pipe (the DMMA tile kernel pads N to 8 and idles on these).  N <= 4, K <= 16.
+// No tile staging, no tensor pipe (the DMMA tile kernel pads N to 8 and idles on these).  N <= 16, K <= 16.
+// When the small operand's legs come first in C a thread's N outputs are ONE contiguous run of 16 N bytes: it is written
+// with 256-bit stores (whole 32-byte sectors per instruction), no shared-memory transpose.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,14 +25,22 @@ struct ApplyParams {
     uint8_t nHoles;               // = k (0, 1 or 2)
     uint8_t holeBit[2];           // bit position of each shared leg inside X's element index, ascending
     uint8_t yFirst;               // 1: C index = y + N * x (small operand is the reference's node A), 0: x + M * y
+    uint8_t lowRun;               // K == 4 and the shared leg is X's leg 0: the four summands are one contiguous 64-byte run
     uint32_t kOff[16];            // element offset inside X of summed value s
-    uint8_t yIdx[16][4];          // element index inside Y of (s, y)
+    uint8_t yIdx[16][16];         // element index inside Y of (s, y)
 };
+
+__device__ __forceinline__ void st_stream_256(double2 *dst, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+__device__ __forceinline__ void ld_stream_256(const double2 *src, double2 &a, double2 &b) {
+    asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(src) : "memory");
+}
 
 template <int K, int N>
 __global__ void __launch_bounds__(256) k_apply(const ApplyParams p) {
     __shared__ double2 W[K * N];
-    __shared__ double2 T[N > 1 ? 256 * (N + 1) : 1];      // yFirst: [x in block][y], row stride N + 1 (conflict-free STS.128)
     for (int i = threadIdx.x; i < K * N; i += blockDim.x) W[i] = p.Y[p.yIdx[i / N][i % N]];
     __syncthreads();
     const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;        // M is a multiple of the block size
@@ -39,8 +49,14 @@ __global__ void __launch_bounds__(256) k_apply(const ApplyParams p) {
     for (int j = 0; j < 2; j++)
         if (j < p.nHoles) { const int h = p.holeBit[j]; off = ((off >> h) << (h + 2)) | (off & ((1ull << h) - 1)); }
     double2 xv[K];
+    if (K == 4 && p.lowRun) {
+        // kOff = {0, 1, 2, 3}: whole sectors with two 256-bit loads instead of four 16-byte loads a sector apart
+        ld_stream_256(p.X + off, xv[0], xv[1]);
+        ld_stream_256(p.X + off + 2, xv[2 % K], xv[3 % K]);
+    } else {
 #pragma unroll
-    for (int s = 0; s < K; s++) xv[s] = __ldcs(p.X + off + p.kOff[s]);        // streamed once: evict-first
+        for (int s = 0; s < K; s++) xv[s] = __ldcs(p.X + off + p.kOff[s]);        // streamed once: evict-first
+    }
     double accR[N], accI[N];
 #pragma unroll
     for (int y = 0; y < N; y++) accR[y] = accI[y] = 0.0;
@@ -55,15 +71,9 @@ __global__ void __launch_bounds__(256) k_apply(const ApplyParams p) {
             accI[y] = fma(xv[s].y, w.x, accI[y]);
         }
     if (N > 1 && p.yFirst) {
+        double2 *c = p.C + x * N;                                              // this thread's run: y fastest
 #pragma unroll
-        for (int y = 0; y < N; y++) T[threadIdx.x * (N + 1) + y] = make_double2(accR[y], accI[y]);
-        __syncthreads();
-        double2 *c = p.C + (uint64_t)blockIdx.x * blockDim.x * N;
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            const int e = j * 256 + threadIdx.x;
-            __stcs(c + e, T[(e / N) * (N + 1) + (e % N)]);
-        }
+        for (int y = 0; y < N; y += 2) st_stream_256(c + y, accR[y], accI[y], accR[y + 1], accI[y + 1]);
     } else {
 #pragma unroll
         for (int y = 0; y < N; y++) __stcs(p.C + x + p.M * y, make_double2(accR[y], accI[y]));

@@ -134,6 +134,12 @@ static bool apply_enabled() {
     return v == 1;
 }
 
+static bool apply16_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_NO_APPLY16"); v = (e && atoi(e)) ? 0 : 1; }
+    return v == 1;
+}
+
 static int choose_kind(const StepGeom &g, GettChoice &gc, int microLog4) {
     const unsigned long long U = g.units();
     if (!disable_micro() && U <= (1ull << (2 * microLog4)) && g.rA <= MICRO_MAX_RANK && g.rB <= MICRO_MAX_RANK && g.rC <= MICRO_MAX_RANK)
@@ -143,7 +149,13 @@ static int choose_kind(const StepGeom &g, GettChoice &gc, int microLog4) {
     // big tensor x tiny tensor (<= 64 elements, <= 4 outputs per free index): a pure stream, one thread per free index.
     // One exception stays with the tile kernel (0.87 vs 1.46 ms at rank 14): both shared legs are the big operand's two
     // lowest legs AND there are four outputs per free index.
-    if (!force_generic() && apply_enabled() && bigFree >= 4 && g.k <= 2 && smallFree <= 1) {
+    // ... and one more member: a rank-3 tensor sharing ONE leg (16 outputs per free index, 4 loads): write-dominated, the
+    // tile kernel is issue-bound on it
+    // (only when the big operand's legs come first in C.  With the small operand's legs first a thread's 16 outputs are a
+    // 256-byte run, lanes 256 bytes apart: 1.27 ms at rank 13; sixteen lanes per free index with broadcast loads: 1.5-2.4 ms;
+    // the tile kernel with its transposed 256-bit stores: 0.96 ms -- that case stays there)
+    if (!force_generic() && apply_enabled() && bigFree >= 4 && g.k <= 2 &&
+        (smallFree <= 1 || (smallFree == 2 && g.k == 1 && g.nfa > g.nfb && apply16_enabled()))) {
         const bool sw = g.nfb > g.nfa;
         const int *posX = sw ? g.posB : g.posA;
         const bool lowPair = g.k == 2 && std::min(posX[0], posX[1]) == 0 && std::max(posX[0], posX[1]) == 1;
@@ -442,8 +454,9 @@ static int launch_apply(qtb_ctx *ctx, const StepGeom &g, bool swap, const double
     }
     // both shared legs are X's two lowest legs: four lanes per output, each reading a 64-byte quarter of the 256-byte run
     if (g.k == 2 && std::min(posX[0], posX[1]) == 0 && std::max(posX[0], posX[1]) == 1) {
-        uint8_t byMem[16][4];
-        for (int sv = 0; sv < K; sv++) memcpy(byMem[p.kOff[sv]], p.yIdx[sv], 4);      // kOff is a permutation of 0..15 here
+        uint8_t byMem[16][16];
+        memset(byMem, 0, sizeof(byMem));
+        for (int sv = 0; sv < K; sv++) memcpy(byMem[p.kOff[sv]], p.yIdx[sv], 16);     // kOff is a permutation of 0..15 here
         memcpy(p.yIdx, byMem, sizeof(byMem));
         const unsigned grid4 = (unsigned)(p.M * 4 / 256);
         if (nfy != 0) return fail(QTB_ERR_INVALID, "step outside the streaming class");
@@ -452,12 +465,15 @@ static int launch_apply(qtb_ctx *ctx, const StepGeom &g, bool swap, const double
         ctx->stats.launches++;
         return QTB_OK;
     }
+    // the single shared leg is X's leg 0: a thread's four summands are one 64-byte run -> two 256-bit loads
+    p.lowRun = (g.k == 1 && posX[0] == 0) ? 1 : 0;
     const unsigned grid = (unsigned)(p.M / 256);
     switch (g.k * 4 + nfy) {
         case 0: k_apply<1, 1><<<grid, 256, 0, s>>>(p); break;
         case 1: k_apply<1, 4><<<grid, 256, 0, s>>>(p); break;
         case 4: k_apply<4, 1><<<grid, 256, 0, s>>>(p); break;
         case 5: k_apply<4, 4><<<grid, 256, 0, s>>>(p); break;
+        case 6: k_apply<4, 16><<<grid, 256, 0, s>>>(p); break;
         case 8: k_apply<16, 1><<<grid, 256, 0, s>>>(p); break;
         case 9: k_apply<16, 4><<<grid, 256, 0, s>>>(p); break;
         default: return fail(QTB_ERR_INVALID, "step outside the streaming class");

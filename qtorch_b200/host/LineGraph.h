@@ -51,6 +51,7 @@ public:
     void SetQBBOutFiles(const std::string &cnfNew, const std::string &qbbOutNew, const std::string &qbbStatsNew) {
         cnfName = cnfNew; qbbOutName = qbbOutNew; qbbStatsName = qbbStatsNew;
     }
+    const std::string &QBBOutFile() const { return qbbOutName; }
     // additions: sizes of L(G) and the cnf text, for tests
     size_t NumLineGraphVertices() const { return GraphWires.size(); }
     size_t NumLineGraphEdges() const { return LGEdges.size(); }

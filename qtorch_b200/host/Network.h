@@ -98,6 +98,7 @@ public:
     // ---- additions (not in the reference) -------------------------------------------------------------
     const std::vector<PlanRecord> &GetPlan() const noexcept { return mPlan; }     // every executed step, in order
     int GetNumOriginalNodes() const noexcept { return mNumOriginalNodes; }          // nodes created by the parser
+    static std::shared_ptr<Node> MakeMeasurementCap(char m, const char **what = nullptr);
     // start the device->host read of the final scalar behind the steps enqueued so far, without waiting for it; a later
     // GetFinalValue() then waits for that copy only.  Lets a caller enqueue the next network while this one still runs.
     void PrefetchFinalValue();
@@ -222,19 +223,25 @@ inline void Network::CreateInitialStates() {
     }
 }
 
+// the rank-1 node that closes a qubit line for measurement character m (reference Network.h:199-237)
+inline std::shared_ptr<Node> Network::MakeMeasurementCap(char m, const char **what) {
+    const char *dummy = nullptr;
+    const char *&w = what ? *what : dummy;
+    switch (m) {
+        case 'X': w = "Creating X measurement on qubit: "; return std::make_shared<XMeasure>();
+        case 'Y': w = "Creating Y measurement on qubit: "; return std::make_shared<YMeasure>();
+        case 'Z': w = "Creating Z measurement on qubit: "; return std::make_shared<ZMeasure>();
+        case '0': w = "Creating Projection |0><0| measurement on qubit: "; return std::make_shared<ProjectZero>();
+        case '1': w = "Creating Projection |1><1| measurement on qubit: "; return std::make_shared<ProjectOne>();
+        default: w = "Tracing out qubit: "; return std::make_shared<TraceNode>();
+    }
+}
+
 inline void Network::AddMeasurementsOrTrace(std::vector<char> &measurements) {
     for (int q = 0; q < mNumberOfQubits; ++q) {
         const char m = (static_cast<int>(measurements.size()) <= q) ? 'T' : measurements[q];
-        std::shared_ptr<Node> cap;
         const char *what = nullptr;
-        switch (m) {
-            case 'X': cap = std::make_shared<XMeasure>(); what = "Creating X measurement on qubit: "; break;
-            case 'Y': cap = std::make_shared<YMeasure>(); what = "Creating Y measurement on qubit: "; break;
-            case 'Z': cap = std::make_shared<ZMeasure>(); what = "Creating Z measurement on qubit: "; break;
-            case '0': cap = std::make_shared<ProjectZero>(); what = "Creating Projection |0><0| measurement on qubit: "; break;
-            case '1': cap = std::make_shared<ProjectOne>(); what = "Creating Projection |1><1| measurement on qubit: "; break;
-            default: cap = std::make_shared<TraceNode>(); what = "Tracing out qubit: "; break;
-        }
+        std::shared_ptr<Node> cap = MakeMeasurementCap(m, &what);
         if (!detail::quietMode()) std::cout << what << q << std::endl;
         mNetworkParsingWires[q]->SetNodeB(cap);
         cap->GetWires().push_back(mNetworkParsingWires[q]);

@@ -12,4 +12,5 @@
 #include "leviParser.hpp"
 #include "preprocess.h"
 #include "Slicing.h"
+#include "PlanCache.h"
 using namespace qtorch;

@@ -42,6 +42,7 @@ def host_library():
         H.qth_engine_ctx.restype = ctypes.c_void_p
         cd, cll, ci = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)
         H.qth_contract_linegraph.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, cd, cll, ci, cd]
+        H.qth_contract_cached.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, cd, cll, ci, ci]
         H.qth_linegraph_begin.restype = ctypes.c_void_p
         H.qth_linegraph_begin.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
         H.qth_linegraph_end.argtypes = [ctypes.c_void_p, cd, cll, ci]
@@ -171,6 +172,19 @@ def contract_linegraph(qasm, measure, ordering, reduce=True):
     if rc != 0:
         _raise(H, rc)
     return complex(v[0], v[1]), flops.value, nodes.value, secs.value
+
+
+def contract_cached(qasm, measure, ordering, reduce=True):
+    """contract_linegraph through the plan cache (host/PlanCache.h): host bookkeeping and plan compilation happen once per
+    (qasm, ordering, reduce); later calls swap the measurement caps and replay the graph.  -> (value, flops, nodes, hit)"""
+    H = host_library()
+    v = (ctypes.c_double * 2)()
+    flops, nodes, hit = ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+    rc = H.qth_contract_cached(qasm.encode(), measure.encode(), (ordering or "").encode(), 1 if reduce else 0, v,
+                               ctypes.byref(flops), ctypes.byref(nodes), ctypes.byref(hit))
+    if rc != 0:
+        _raise(H, rc)
+    return complex(v[0], v[1]), flops.value, nodes.value, bool(hit.value)
 
 
 class LinegraphJob:

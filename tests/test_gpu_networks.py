@@ -189,3 +189,29 @@ def test_cost_based_planner_value(built, name):
     val = complex(float(out["value"][0]), float(out["value"][1]))
     assert _close(val, c["value"]), (val, c["value"])
     assert out["plan"] == c["plan"] and int(out["flops"][0]) == c["flops"]
+
+
+@pytest.mark.gpu
+def test_plan_cache_replays_one_compiled_plan_for_many_measurements(built, networks):
+    """host/PlanCache.h: the plan depends on (circuit topology, ordering), not on the measurement string -- the three
+    test_JW observables share ONE compiled plan (first call compiles, the others are cache hits) and still match the
+    reference's values, which it computed with a separate ordering per observable"""
+    from qtorch_b200 import host_api
+    first = networks["testJW_XXXX"]
+    _, qasm, _, ordering = golden_paths(first)
+    qasm = os.path.join(GOLDEN, first["qasm"])
+    hits = []
+    for name in ("testJW_XXXX", "testJW_YXXY", "testJW_Z0", "testJW_XXXX"):
+        rec = networks[name]
+        v, flops, nodes, hit = host_api.contract_cached(qasm, os.path.join(GOLDEN, rec["measure"]), ordering, True)
+        ref = complex(*rec["value"])
+        assert abs(v - ref) <= 1e-10 * max(1.0, abs(ref)), (name, v, ref)
+        assert flops == first["flops"] and nodes == first["nodes"]
+        hits.append(hit)
+    assert hits == [False, True, True, True]
+    # GHZ-1000: zeros and ones on one compiled plan
+    z, o = networks["ghz1000_zeros"], networks["ghz1000_ones"]
+    gq, go = os.path.join(GOLDEN, z["qasm"]), os.path.join(GOLDEN, z["ordering"])
+    for rec in (z, o, z):
+        v, flops, nodes, hit = host_api.contract_cached(gq, os.path.join(GOLDEN, rec["measure"]), go, True)
+        assert abs(v - complex(*rec["value"])) <= 1e-10 and flops == rec["flops"]

@@ -309,6 +309,11 @@ def test_fused_dmma_step_plus_inner_product(engine, t_is_a, shape):
     (9, 2, [2, 7], [0, 1]),             # K=16, N=1
     (9, 3, [0, 8], [2, 0]),             # K=16, N=4
     (3, 9, [0, 2], [8, 3]),             # K=16, N=4, small operand first, its shared legs out of order in the big one
+    (9, 3, [4], [1]),                   # rank-3 tensor sharing one leg: K=4, N=16, big operand first
+    (9, 3, [0], [2]),                   # ... shared leg = the big operand's leg 0 (one 64-byte run per index: 256-bit loads)
+    (3, 9, [1], [6]),                   # K=4, N=16, small operand first: tile kernel (transposed 256-bit stores)
+    (9, 2, [0], [0]),                   # K=4, N=4 with the shared leg at the bottom: 256-bit loads
+    (2, 9, [1], [0]),                   # ... small operand first: 256-bit loads and 256-bit stores
     (8, 1, [], []),                     # outer product with a rank-1 tensor: K=1, N=4
     (1, 8, [], []),                     # outer product, small first: C = y + 4 x
     (10, 0, [], []),                    # scaling by a scalar tensor: K=1, N=1
@@ -321,7 +326,8 @@ def test_streaming_apply_steps(engine, rA, rB, pA, pB):
     kinds = [t["kernel"] for t in engine.read_trace() if t["kernel"] != 0]       # (uploads ride in a grouped launch: code 0)
     engine.trace(False)
     if os.environ.get("QTB_NO_APPLY") != "1":
-        assert kinds == [2 if (len(pA) == 2 and min(rA, rB) == 3 and sorted(pA if rA > rB else pB) == [0, 1]) else 7], kinds
+        tile = (len(pA) == 2 and min(rA, rB) == 3 and sorted(pA if rA > rB else pB) == [0, 1]) or (len(pA) == 1 and rA == 3 and rB > 3)
+        assert kinds == [2 if tile else 7], kinds
 
 
 def test_tile_kernels_without_the_streaming_class():

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/prof_sliced.py [slice_wires] -- where one index-sliced amplitude of BASELINE config 2 spends its time: per-segment
+"""tools/prof_sliced.py [slice_wires] [network] -- where one index-sliced amplitude (default: the config-2 term) spends its time: per-segment
 CUDA-event trace of the invariant prefix (run once) and of one pass over the per-slice suffix, then the untraced timing."""
 import json
 import os
@@ -10,7 +10,7 @@ import qtorch_b200 as qt
 from qtorch_b200 import host_api, slicing
 
 G = os.path.join(ROOT, "tests", "golden")
-rec = json.load(open(os.path.join(G, "networks.json")))["qaoa30_z27z29"]
+rec = json.load(open(os.path.join(G, "networks.json")))[sys.argv[2] if len(sys.argv) > 2 else "qaoa30_z27z29"]
 s = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 ranks, steps, inputs, flops = host_api.export_plan_linegraph(os.path.join(G, rec["qasm"]), os.path.join(G, rec["measure"]), os.path.join(G, rec["ordering"]), True)
 wires = slicing.choose_wires(ranks, steps, s)
@@ -26,7 +26,7 @@ eng.trace(True)
 plan.run_slots([0])
 tr = eng.read_trace()
 eng.trace(False)
-names = {0: "micro", 1: "thread", 2: "gett", 3: "warp", 5: "reduce", 6: "fused"}
+names = {0: "micro", 1: "thread", 2: "gett", 3: "warp", 5: "reduce", 6: "fused", 7: "apply"}
 tot = 0.0
 for t in tr:
     tot += t["ms"]
