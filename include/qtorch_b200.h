@@ -204,6 +204,7 @@ typedef struct qtb_stats {
     long long units;             /* sum 4^(rC+k) over executed steps                                     */
     long long bytes_h2d, bytes_d2h;
     long long pool_bytes_reserved, pool_bytes_peak_live;
+    long long tma_launches;      /* ... of the launches: tile-kernel steps whose operand tiles were fed by TMA         */
 } qtb_stats;
 int qtb_ctx_stats(qtb_ctx *ctx, qtb_stats *out);
 int qtb_ctx_reset_stats(qtb_ctx *ctx);

@@ -50,7 +50,7 @@ class PlanStep(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_longlong) for n in ("launches", "steps", "micro_steps", "units", "bytes_h2d", "bytes_d2h",
-                                                  "pool_bytes_reserved", "pool_bytes_peak_live")]
+                                                  "pool_bytes_reserved", "pool_bytes_peak_live", "tma_launches")]
 
 
 class StepTrace(ctypes.Structure):

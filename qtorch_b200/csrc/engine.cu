@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,7 @@
 #include "step.h"
 #include "kernels.cuh"
 #include "gett.cuh"
+#include "gett_tma.cuh"
 #include "reduce.cuh"
 #include "apply.cuh"
 
@@ -275,6 +277,189 @@ static void add_fusion(const StepGeom &g2, bool tIsA, const double2 *D, double2 
     for (int j = 0; j < RB; j++) v.push_back({p.shDy[j], TMB + j});
     std::sort(v.begin(), v.end(), [](const CB &a, const CB &b) { return a.shift < b.shift; });
     for (size_t j = 0; j < v.size(); j++) p.permD[j] = (uint8_t)v[j].coord;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed tile kernel (gett_tma.cuh): eligibility, role assignment and tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)sym;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+// Opt-in (QTB_TMA=1): measured on B200 the TMA-fed variant is correct but 7 % (tile = one contiguous 16 KB run) to 19 %
+// (tile legs picked for eligibility, 64-byte pieces) SLOWER than the cp.async gather on the config-2 rank-14 steps
+// (profiles/r02_tma.txt), so the default path stays the cp.async ring.
+static bool tma_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_TMA"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
+
+
+// the TMA instantiation: 3M complex product, 64x64x16 tiles, 16 math warps of 16x16, 6 ring stages of 32 KB
+typedef GettTmaCfg<4, 4, 2, 2, 16, 6, 1> TmaCfg;
+static void (*const g_gettTmaFn)(const GettTmaParams) = k_gett_tma<4, 4, 2, 2, 16, 6, 1>;
+
+struct TileLeg { int pos; int role; int logical; };         // role 0: free (x or y), 1: shared (k); logical: index among the tile's legs of that role
+
+// dense-index bit -> its contribution to the 16-byte bank group of a 64-byte-swizzled slot (see gett_tma.cuh):
+// slot = idx ^ ((idx >> 3) & 3)
+static int swizzle_vec(int p) { return p < 3 ? (1 << p) : (p < 5 ? (1 << (p - 3)) : 0); }
+static bool independent3(int a, int b, int c) {
+    if (!a || !b || !c) return false;
+    return a != b && a != c && b != c && (a ^ b) != c;
+}
+
+// the tile must hold the operand's leg 0 (it is the contiguous inner dimension of the box); the other legs form runs of
+// memory-adjacent legs -> tensor-map dimensions (at most four legs each); dense-index bit of every tile bit
+struct OperandTile {
+    std::vector<TileLeg> legs;                    // ascending position
+    std::vector<std::pair<int, int>> dims;        // (first leg position, number of legs <= 4)
+    int bitOf(int role, int logical, int b) const {
+        for (size_t j = 0; j < legs.size(); j++) if (legs[j].role == role && legs[j].logical == logical) return 2 * (int)j + b;
+        return -1;
+    }
+};
+static bool analyse_tile(std::vector<TileLeg> legs, OperandTile &out) {
+    std::sort(legs.begin(), legs.end(), [](const TileLeg &a, const TileLeg &b) { return a.pos < b.pos; });
+    out.legs = legs;
+    out.dims.clear();
+    if (legs.empty() || legs[0].pos != 0) return false;
+    for (size_t j = 1; j < legs.size();) {
+        size_t e = j + 1;
+        while (e < legs.size() && legs[e].pos == legs[e - 1].pos + 1) e++;
+        for (size_t c = j; c < e; c += 4) out.dims.push_back({legs[c].pos, (int)std::min<size_t>(4, e - c)});
+        j = e;
+    }
+    return out.dims.size() <= 3;
+}
+
+static int encode_tile_map(CUtensorMap *tm, const double2 *base, int rank, const OperandTile &t) {
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc) return fail(QTB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+    // dim0 = leg 0 x (re, im): 8 doubles = one 64-byte swizzle row; dim1 = the "offset" dimension in units of 4 elements
+    cuuint64_t gdim[5] = {8, (cuuint64_t)1 << (2 * (rank - 1)), 1, 1, 1};
+    cuuint64_t gstr[4] = {64, 0, 0, 0};
+    cuuint32_t box[5] = {8, 1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+    for (int d = 0; d < 3; d++) {
+        if (d < (int)t.dims.size()) {
+            gdim[2 + d] = (cuuint64_t)1 << (2 * t.dims[d].second);
+            gstr[1 + d] = (cuuint64_t)16 << (2 * t.dims[d].first);
+            box[2 + d] = (cuuint32_t)gdim[2 + d];
+        } else {
+            gstr[1 + d] = (cuuint64_t)16 << (2 * rank);       // unused dimension: size 1 beyond the tensor
+        }
+    }
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<double2 *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(QTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return QTB_OK;
+}
+
+// Tries to set up the TMA-fed variant for a compute-bound tile step.  Returns false when the step does not qualify (too few
+// free / shared legs for full 64 x 64 x 16 tiles, more than three runs per operand tile, no conflict-free role assignment,
+// tensors of more than 2^31 elements): the caller then uses the cp.async gather of gett.cuh.
+static bool build_gett_tma(const StepGeom &g, bool sw, const double2 *A, const double2 *B, double2 *C, GettTmaParams &P) {
+    if (!tma_enabled() || !tma_encoder()) return false;
+    const int TMB = 6, TNB = 6, TKB = 4;                                  // 64 x 64 x 16
+    const int nfx = sw ? g.nfb : g.nfa, nfy = sw ? g.nfa : g.nfb;
+    const int rX = sw ? g.rB : g.rA, rY = sw ? g.rA : g.rB;
+    if (nfx < 3 || nfy < 3 || g.k < 2 || rX > 15 || rY > 15) return false;
+    const int *freeX = sw ? g.freeB : g.freeA, *freeY = sw ? g.freeA : g.freeB;
+    const int *posX = sw ? g.posB : g.posA, *posY = sw ? g.posA : g.posB;
+    const int cx0 = sw ? g.nfa : 0, cy0 = sw ? 0 : g.nfa;
+    int ord[QTB_MAXR];
+    for (int j = 0; j < g.k; j++) ord[j] = j;
+    std::stable_sort(ord, ord + g.k, [&](int a, int b) { return std::min(posX[a], posY[a]) < std::min(posX[b], posY[b]); });
+    // candidate leg triples of an operand: its three lowest free legs, then every triple of its ten lowest that keeps the lowest
+    auto candidates = [](int nf) {
+        std::vector<std::array<int, 3>> out;
+        out.push_back({0, 1, 2});
+        const int m = std::min(nf, 10);
+        for (int b = 1; b < m; b++) for (int c = b + 1; c < m; c++) if (!(b == 1 && c == 2)) out.push_back({0, b, c});
+        return out;
+    };
+    for (const auto &xc : candidates(nfx)) {
+        for (const auto &yc : candidates(nfy)) {
+            OperandTile tx, ty;
+            std::vector<TileLeg> lx, ly;
+            for (int i = 0; i < 3; i++) { lx.push_back({freeX[xc[i]], 0, i}); ly.push_back({freeY[yc[i]], 0, i}); }
+            for (int l = 0; l < 2; l++) { lx.push_back({posX[ord[l]], 1, l}); ly.push_back({posY[ord[l]], 1, l}); }
+            if (!analyse_tile(lx, tx) || !analyse_tile(ly, ty)) continue;
+            // roles: two k bits for (t0, t1) -- the same pair in both operands -- and one free bit per operand for g0
+            int t0l = -1, t0b = 0, t1l = 0, t1b = 0, gxl = 0, gxb = 0, gyl = 0, gyb = 0;
+            for (int a = 0; a < 4 && t0l < 0; a++) for (int b = 0; b < 4 && t0l < 0; b++) {
+                if (a == b) continue;
+                const int vx0 = swizzle_vec(tx.bitOf(1, a / 2, a % 2)), vx1 = swizzle_vec(tx.bitOf(1, b / 2, b % 2));
+                const int vy0 = swizzle_vec(ty.bitOf(1, a / 2, a % 2)), vy1 = swizzle_vec(ty.bitOf(1, b / 2, b % 2));
+                int fx = -1, fy = -1;
+                for (int c = 0; c < 6 && fx < 0; c++) if (independent3(swizzle_vec(tx.bitOf(0, c / 2, c % 2)), vx0, vx1)) fx = c;
+                for (int c = 0; c < 6 && fy < 0; c++) if (independent3(swizzle_vec(ty.bitOf(0, c / 2, c % 2)), vy0, vy1)) fy = c;
+                if (fx >= 0 && fy >= 0) { t0l = a / 2; t0b = a % 2; t1l = b / 2; t1b = b % 2; gxl = fx / 2; gxb = fx % 2; gyl = fy / 2; gyb = fy % 2; }
+            }
+            if (t0l < 0) continue;
+            // ---- fill the parameters
+            memset(&P, 0, sizeof(P));
+            GettParams &p = P.g;
+            p.X = sw ? B : A; p.Y = sw ? A : B; p.C = C;
+            p.xbits = 2 * nfx; p.ybits = 2 * nfy; p.kbits = 2 * g.k;
+            p.nyValid = 64; p.nyBits = 6;
+            // logical k bits: t0, t1, then the chunk's other two bits, then the remaining shared legs (k-chunk index)
+            struct KB { int l, b; };
+            std::vector<KB> kb = {{t0l, t0b}, {t1l, t1b}};
+            for (int a = 0; a < 4; a++) if (!((a / 2 == t0l && a % 2 == t0b) || (a / 2 == t1l && a % 2 == t1b))) kb.push_back({a / 2, a % 2});
+            for (int j = 0; j < TKB; j++) {
+                p.shXk[j] = (uint8_t)(2 * posX[ord[kb[j].l]] + kb[j].b); p.shYk[j] = (uint8_t)(2 * posY[ord[kb[j].l]] + kb[j].b);
+                P.ikX[j] = (uint8_t)tx.bitOf(1, kb[j].l, kb[j].b); P.ikY[j] = (uint8_t)ty.bitOf(1, kb[j].l, kb[j].b);
+            }
+            for (int j = 2; j < g.k; j++) for (int b = 0; b < 2; b++) { p.shXk[2 * j + b] = (uint8_t)(2 * posX[ord[j]] + b); p.shYk[2 * j + b] = (uint8_t)(2 * posY[ord[j]] + b); }
+            // logical x bits: g0 first, then the tile's other five bits by C significance, then the remaining free legs (tile index)
+            auto fillFree = [&](const std::array<int, 3> &cand, const int *freeLegs, int nf, int c0, int g0l, int g0b, const OperandTile &t,
+                                uint8_t *shOp, uint8_t *shC, uint8_t *idxPos) {
+                struct FB { int shOp, shC, idx; };
+                std::vector<FB> bits;
+                bits.push_back({2 * freeLegs[cand[g0l]] + g0b, 2 * (c0 + cand[g0l]) + g0b, t.bitOf(0, g0l, g0b)});
+                std::vector<FB> rest;
+                for (int l = 0; l < 3; l++) for (int b = 0; b < 2; b++) if (!(l == g0l && b == g0b)) rest.push_back({2 * freeLegs[cand[l]] + b, 2 * (c0 + cand[l]) + b, t.bitOf(0, l, b)});
+                std::sort(rest.begin(), rest.end(), [](const FB &a, const FB &b) { return a.shC < b.shC; });
+                bits.insert(bits.end(), rest.begin(), rest.end());
+                for (int j = 0; j < 6; j++) { shOp[j] = (uint8_t)bits[j].shOp; shC[j] = (uint8_t)bits[j].shC; idxPos[j] = (uint8_t)bits[j].idx; }
+                int n = 6;
+                for (int f = 0; f < nf; f++) {
+                    if (f == cand[0] || f == cand[1] || f == cand[2]) continue;
+                    for (int b = 0; b < 2; b++) { shOp[n] = (uint8_t)(2 * freeLegs[f] + b); shC[n] = (uint8_t)(2 * (c0 + f) + b); n++; }
+                }
+            };
+            fillFree(xc, freeX, nfx, cx0, gxl, gxb, tx, p.shXx, p.shCx, P.ixX);
+            fillFree(yc, freeY, nfy, cy0, gyl, gyb, ty, p.shYy, p.shCy, P.iyY);
+            const unsigned long long Mx = 1ull << p.xbits, Ny = 1ull << p.ybits, K = 1ull << p.kbits;
+            p.nTilesX = (uint32_t)(Mx / 64); p.nTilesY = (uint32_t)(Ny / 64); p.nChunks = (uint32_t)(K / 16);
+            auto swz = [](uint32_t idx) { return (uint16_t)((idx ^ ((idx >> 3) & 3u)) << 4); };
+            for (int i = 0; i < 4; i++) {            // x (y) advances by 8 per fragment index: logical bits 3, 4
+                uint32_t ix = 0, iy = 0;
+                for (int b = 0; b < 2; b++) if ((i >> b) & 1) { ix |= 1u << P.ixX[3 + b]; iy |= 1u << P.iyY[3 + b]; }
+                P.cXi[i] = swz(ix); P.cYj[i] = swz(iy);
+            }
+            for (int kk = 0; kk < 4; kk++) {         // k advances by 4 per k-step: logical k bits 2, 3
+                uint32_t ix = 0, iy = 0;
+                for (int b = 0; b < 2; b++) if ((kk >> b) & 1) { ix |= 1u << P.ikX[2 + b]; iy |= 1u << P.ikY[2 + b]; }
+                P.cXkk[kk] = swz(ix); P.cYkk[kk] = swz(iy);
+            }
+            if (encode_tile_map(&P.tmX, p.X, rX, tx) != QTB_OK || encode_tile_map(&P.tmY, p.Y, rY, ty) != QTB_OK) return false;
+            (void)TMB; (void)TNB;
+            return true;
+        }
+    }
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -712,6 +897,19 @@ static int enqueue_fused(qtb_ctx *ctx, const StepGeom &g1, const GettChoice &gc1
 static int enqueue_big(qtb_ctx *ctx, const StepGeom &g, int kind, const GettChoice &gc, const double2 *A, const double2 *B,
                        double2 *C, cudaStream_t s) {
     if (kind == KIND_GETT) {
+        // compute-bound class on full 64 x 64 x 16 tiles: operand tiles by TMA when the leg placement allows it
+        if (gc.cfg == 7) {
+            GettTmaParams P;
+            if (build_gett_tma(g, gc.swap, A, B, C, P)) {
+                const unsigned nTiles = P.g.nTilesX * P.g.nTilesY;
+                const unsigned grid = std::min<unsigned>(nTiles, (unsigned)ctx->numSMs);
+                g_gettTmaFn<<<grid, TmaCfg::NT, TmaCfg::SMEM, s>>>(P);
+                CU(cudaGetLastError());
+                ctx->stats.launches++;
+                ctx->stats.tma_launches++;
+                return QTB_OK;
+            }
+        }
         GettParams p;
         build_gett(g, gc, A, B, C, p);
         return launch_gett(ctx, p, gc.cfg, s);
@@ -775,6 +973,7 @@ static int ctx_init(qtb_ctx *ctx, int device) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inst.fn, inst.NT, inst.smem));
         inst.occ = std::max(1, occ);
     }
+    CU(cudaFuncSetAttribute(g_gettTmaFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaCfg::SMEM));
     CU(cudaDeviceSynchronize());
     return QTB_OK;
 }

@@ -390,3 +390,36 @@ def test_fused_intermediate_is_single_use(engine):
     assert e.value.status == 2
     for t in (ta, tb, td, tt, out):
         t.free()
+
+
+def test_tma_fed_tile_kernel_matches_the_oracle():
+    """QTB_TMA=1: compute-bound steps whose operand tiles qualify run on k_gett_tma (gett_tma.cuh: one cp.async.bulk.tensor
+    box per operand and ring stage, 64-byte swizzle, host-searched fragment roles).  Opt-in because it measured slower than
+    the cp.async gather; it must still be right, and it must actually be taken (tma_launches).  The switch is read once per
+    process, hence the child."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np
+import qtorch_b200 as qt
+from oracle import oracle as O
+eng = qt.Engine(0)
+rng = np.random.default_rng(11)
+O.lib().qto_set_threads(8)
+taken = 0
+for rA, rB, pA, pB in [(8, 8, [0, 2, 5], [1, 7, 6]), (6, 10, [0, 2, 3], [2, 7, 9]), (8, 6, [0, 4], [2, 5]), (7, 9, [0, 4, 6], [6, 8, 5]),
+                       (10, 6, [2, 5, 9], [0, 2, 3]), (7, 8, [0, 1], [0, 3]), (9, 7, [1, 4, 5], [5, 2, 3])]:
+    A = rng.standard_normal(4 ** rA) + 1j * rng.standard_normal(4 ** rA)
+    B = rng.standard_normal(4 ** rB) + 1j * rng.standard_normal(4 ** rB)
+    eng.reset_stats()
+    C = eng.contract(eng.tensor(rA, A), eng.tensor(rB, B), pA, pB).download()
+    taken += eng.stats()["tma_launches"]
+    ref = O.contract(A, rA, B, rB, pA, pB)
+    assert np.abs(C - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (rA, rB, pA, pB)
+assert taken >= 3, taken
+print("tma steps", taken)
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, QTB_TMA="1", QTORCH_QUIET="1"))
+    assert r.returncode == 0 and "tma steps" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
