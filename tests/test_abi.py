@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_struct_layouts_match_header(built):
     assert ctypes.sizeof(qt.PlanStep) == 12 + 2 * qt.QTB_MAX_RANK
-    assert ctypes.sizeof(qt.Stats) == 8 * 8
+    assert ctypes.sizeof(qt.Stats) == 9 * 8
     assert ctypes.sizeof(qt.StepTrace) == 20
 
 
