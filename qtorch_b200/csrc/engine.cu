@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "gett.cuh"
 #include "gett_tma.cuh"
+#include "gett3m.cuh"
 #include "reduce.cuh"
 #include "apply.cuh"
 
@@ -54,7 +55,7 @@ struct GettChoice { int cfg; bool swap; };      // cfg: 0 C1/TK16 1 C1/TK4 2 C2/
 typedef void (*GettKernel)(const GettParams);
 struct GettInst { GettKernel fn; int TM, TN, TK, NT; size_t smem; int occ; int drows; };   // drows: dotD rows per ring stage (fused variants)
 // C1: 128x64 tile, compute-bound big x big;  C2: 256x16;  C3: 256x8 (N <= 4 padded) -- streaming
-static GettInst g_gett[11] = {
+static GettInst g_gett[15] = {
     {k_gett<4, 2, 4, 4, 16, 3>, 128, 64, 16, GettCfg<4, 2, 4, 4, 16, 3>::NT, GettCfg<4, 2, 4, 4, 16, 3>::SMEM, 1},
     {k_gett<4, 2, 4, 4, 4, 12>, 128, 64, 4, GettCfg<4, 2, 4, 4, 4, 12>::NT, GettCfg<4, 2, 4, 4, 4, 12>::SMEM, 1},
     {k_gett<8, 1, 4, 2, 16, 2>, 256, 16, 16, GettCfg<8, 1, 4, 2, 16, 2>::NT, GettCfg<8, 1, 4, 2, 16, 2>::SMEM, 1},
@@ -70,8 +71,17 @@ static GettInst g_gett[11] = {
     // fused with the inner product that follows (FUSE = 1): variants of 6 (4M) and 7 (3M)
     {k_gett<4, 4, 4, 2, 16, 3, 0, 1>, 128, 64, 16, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::NT, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::SMEM, 1, GettCfg<4, 4, 4, 2, 16, 3, 0, 1>::DROWS},
     {k_gett<4, 4, 2, 2, 16, 5, 1, 1>, 64, 64, 16, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::NT, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::SMEM, 1, GettCfg<4, 4, 2, 2, 16, 5, 1, 1>::DROWS},
+    // 3M with shared operand sums (gett3m.cuh, opt-in QTB_GETT_C1=5): 11 + 2 v plain, 12 + 2 v fused; v = QTB_G3: 0 = 5 ring stages, 1 = 4
+#define G3(ST, SD, F) {k_gett3s<ST, SD, F>, 64, 64, 16, Gett3Cfg<ST, SD, F>::NT, Gett3Cfg<ST, SD, F>::SMEM, 1, Gett3Cfg<ST, SD, F>::DROWS}
+    G3(5, 3, 0), G3(5, 3, 1), G3(4, 3, 0), G3(4, 3, 1),
+#undef G3
 };
-static int fused_variant_of(int cfg) { return cfg == 6 ? 9 : cfg == 7 ? 10 : -1; }
+static int fused_variant_of(int cfg) { return cfg == 6 ? 9 : cfg == 7 ? 10 : (cfg >= 11 && ((cfg - 11) & 1) == 0) ? cfg + 1 : -1; }
+static int g3_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_G3"); v = e ? std::max(0, std::min(1, atoi(e))) : 0; }
+    return v;
+}
 static bool fusion_enabled() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("QTB_FUSE_DOT"); v = (e && !atoi(e)) ? 0 : 1; }
@@ -79,7 +89,9 @@ static bool fusion_enabled() {
 }
 static int c1_variant() {
     static int v = -1;
-    // 2 = "3M" complex product, 16 math warps (default);  3 = 3M, 8 math warps;  1 = 4M, 16 math warps;  0 = 4M, 8 math warps
+    // 2 = "3M" complex product, 16 math warps, every warp adds its own operand sums (default);  5 = 3M with shared operand
+    // sums (gett3m.cuh; correct, measured slower: profiles/r02_g3_shared_sums.txt);  3 = 3M, 8 math warps;  1 = 4M, 16 math
+    // warps;  0 = 4M, 8 math warps
     if (v < 0) { const char *e = getenv("QTB_GETT_C1"); v = e ? atoi(e) : 2; }
     return v;
 }
@@ -166,7 +178,8 @@ static int choose_kind(const StepGeom &g, GettChoice &gc, int microLog4) {
     if (!force_generic() && bigFree >= 4 && g.k >= 1) {
         gc.swap = g.nfb > g.nfa;
         const int tk4 = (g.k == 1) ? 1 : 0;
-        if (smallFree >= 3) gc.cfg = (tk4 == 0 && c1_variant() == 3) ? 8 : (tk4 == 0 && c1_variant() == 2) ? 7 : (tk4 == 0 && c1_variant() == 1) ? 6 : 0 + tk4;
+        if (smallFree >= 3) gc.cfg = (tk4 == 0 && c1_variant() == 3) ? 8 : (tk4 == 0 && c1_variant() == 5) ? 11 + 2 * g3_variant() : (tk4 == 0 && c1_variant() == 2) ? 7 :
+                                     (tk4 == 0 && c1_variant() == 1) ? 6 : 0 + tk4;
         else if (smallFree == 2) gc.cfg = 2 + tk4;
         else gc.cfg = 4 + tk4;
         return KIND_GETT;
@@ -898,7 +911,7 @@ static int enqueue_big(qtb_ctx *ctx, const StepGeom &g, int kind, const GettChoi
                        double2 *C, cudaStream_t s) {
     if (kind == KIND_GETT) {
         // compute-bound class on full 64 x 64 x 16 tiles: operand tiles by TMA when the leg placement allows it
-        if (gc.cfg == 7) {
+        if (gc.cfg == 7 || gc.cfg >= 11) {
             GettTmaParams P;
             if (build_gett_tma(g, gc.swap, A, B, C, P)) {
                 const unsigned nTiles = P.g.nTilesX * P.g.nTilesY;

@@ -423,3 +423,18 @@ print("tma steps", taken)
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, QTB_TMA="1", QTORCH_QUIET="1"))
     assert r.returncode == 0 and "tma steps" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+@pytest.mark.gpu
+def test_shared_sum_tile_kernel_matches_the_oracle():
+    """QTB_GETT_C1=5: the compute-bound class on k_gett3s (gett3m.cuh: XOR-swizzled unpadded operand tiles, the 3M operand sums
+    formed once per tile by the math warps in turn and shared through `summed` mbarriers), plain and fused with the inner
+    product that follows, both ring depths.  Opt-in because it measured slower than k_gett (profiles/r02_g3_shared_sums.txt);
+    it must still be right.  The switch is read once per process, hence the child."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for g3 in ("0", "1"):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_g3.py"), "--parity-only"], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, QTB_GETT_C1="5", QTB_G3=g3, QTORCH_QUIET="1"))
+        assert r.returncode == 0 and "parity failures: 0" in r.stdout and "WRONG" not in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
