@@ -760,13 +760,36 @@ static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std:
         for (uint32_t c = 0; c < nChunks; c++) perLevel[0].push_back({idx, c});
         idx++;
     }
+    // Lane layout of a step (k_micro): G = 2^lg lanes share one output along the summed index, 32 / G outputs per pass, 2^lp <= 4
+    // passes per item.  G is at least 32 / NC (tiny results still use the whole warp) and grows while one item's serial
+    // multiply-add chain is longer than a fair share of its level: a level lasts as long as its slowest warp, and a step with
+    // few outputs and a long sum (a QAOA p=2 term has (NC, K) = (256, 256) steps alone in their level) would otherwise keep
+    // 2 of the CTA's 32 warps busy for 1024 dependent FMAs per lane.
+    std::vector<double> levelWork(nLevels, 0.0);
+    for (const auto &s : steps) levelWork[s.level] += (double)(1ull << (2 * (s.st.rC + s.st.k))) / 32.0;
+    struct Heavy { uint32_t serial; MicroItem it; };
+    std::vector<std::vector<Heavy>> sorted(nLevels);
     for (const auto &s : steps) {
         all[idx] = s.st;
         const uint32_t NC = 1u << (2 * s.st.rC), K = 1u << (2 * s.st.k);
-        const uint32_t nChunks = (NC + QTB_MICRO_CHUNK - 1) / QTB_MICRO_CHUNK;
-        (void)K;
-        for (uint32_t c = 0; c < nChunks; c++) perLevel[s.level].push_back({idx, c});
+        uint32_t lg = 0, lp = 2;                                          // lanes per output 2^lg, passes per item 2^lp
+        while ((32u >> lg) > NC) lg++;                                    // P = 32 / G <= NC
+        while (lp > 0 && ((32u >> lg) << lp) > NC) lp--;                  // passes * P <= NC
+        const uint32_t target = (uint32_t)std::max(16.0, levelWork[s.level] / (QTB_MICRO_THREADS / 32));
+        auto serialOf = [&](uint32_t l, uint32_t q) { return (1u << q) * std::max<uint32_t>(1u, K >> l); };
+        while (serialOf(lg, lp) > target) {                               // fewer passes first (more items, same lanes per output)
+            if (lp > 0) lp--;
+            else if (lg < 5 && (2u << lg) <= K) { lg++; }
+            else break;
+        }
+        const uint32_t perItem = (32u >> lg) << lp;                       // outputs of one item
+        const uint32_t nChunks = NC / perItem;
+        for (uint32_t c = 0; c < nChunks; c++) sorted[s.level].push_back({serialOf(lg, lp), {idx, c | (lg << 24) | (lp << 29)}});
         idx++;
+    }
+    for (uint32_t l = 0; l < nLevels; l++) {                              // heaviest items first: warps take items round-robin
+        std::stable_sort(sorted[l].begin(), sorted[l].end(), [](const Heavy &a, const Heavy &b) { return a.serial > b.serial; });
+        for (const auto &h : sorted[l]) perLevel[l].push_back(h.it);
     }
     uint32_t nItems = 0;
     for (auto &v : perLevel) nItems += (uint32_t)v.size();

@@ -120,7 +120,7 @@ struct MicroHeader {
     uint32_t prefetchBytes;       // size of the operand region to pull into L2 up front (0 = none)
     uint64_t prefetchPtr;         // device address of that region (plan input blob / upload payload)
 };
-struct MicroItem { uint32_t step; uint32_t chunk; };
+struct MicroItem { uint32_t step; uint32_t chunk; };      // chunk: bits 0-23 index of the item inside its step, bits 24-28 log2 of the lanes per output, bits 29-30 log2 of the passes
 
 // per-warp scratch in dynamic shared memory: the step descriptor (so leg tables are not re-read from global memory
 // for every index) and the offsets of all summed terms when K <= QTB_MICRO_TAB
@@ -198,15 +198,17 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
                 }
                 __syncwarp();
             }
-            // lane layout: NC >= 32 -> one output per lane (4 passes per 128-output chunk); NC < 32 -> the 32 lanes
-            // cover (output, slice of the summed index) and a shuffle tree adds the slices, so tiny results still
-            // use the whole warp.  The summed loop is unrolled so several independent loads are in flight.
-            const uint32_t G = NC >= 32 ? 1u : 32u / NC;                 // lanes per output along s
-            const uint32_t sg = NC >= 32 ? 0u : (uint32_t)lane / NC;
-            const int passes = NC >= 32 ? QTB_MICRO_CHUNK / 32 : 1;
+            // lane layout (chosen by the host, build_micro_blob): G = 2^lg lanes cover one output along the summed index and a
+            // shuffle tree adds their slices; P = 32 / G outputs per pass, 2^lp <= 4 passes per item.  Tiny results (NC < 32) and
+            // steps with few outputs but long sums use the whole warp -- and more warps of the CTA -- this way.  The summed loop
+            // is unrolled so several independent loads are in flight.
+            const uint32_t lg = (item.chunk >> 24) & 31u, lp = item.chunk >> 29, chunk = item.chunk & 0xffffffu;
+            const uint32_t G = 1u << lg, P = 32u >> lg;
+            const uint32_t sg = (uint32_t)lane >> (5 - lg);
+            const int passes = 1 << lp;
 #pragma unroll 1
             for (int j = 0; j < passes; j++) {
-                const uint32_t c = NC >= 32 ? item.chunk * QTB_MICRO_CHUNK + j * 32 + lane : ((uint32_t)lane & (NC - 1));
+                const uint32_t c = ((chunk << lp) + (uint32_t)j) * P + ((uint32_t)lane & (P - 1));
                 double cr = 0.0, ci = 0.0;
                 if (c < NC) {
                     uint64_t ba, bb;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
                         }
                     }
                 }
-                for (uint32_t off = NC; off < 32; off <<= 1) {           // no-op when NC >= 32
+                for (uint32_t off = P; off < 32; off <<= 1) {            // no-op when G = 1
                     cr += __shfl_xor_sync(0xffffffffu, cr, off);
                     ci += __shfl_xor_sync(0xffffffffu, ci, off);
                 }

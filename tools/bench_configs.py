@@ -74,11 +74,32 @@ def time_plan_replay(name, reps=50):
     plan.destroy()
 
 
+def time_cached(name, reps=20):
+    """the same call through the plan cache (host/PlanCache.h): parse + reduce + ordering walk + plan compilation once, then one
+    small H2D (the caps), one graph launch and one 16-byte D2H per evaluation"""
+    rec = NETS[name]
+    qasm, meas, ordering = (os.path.join(G, rec[k]) for k in ("qasm", "measure", "ordering"))
+    t0 = time.perf_counter()
+    val, flops, nodes, hit = host_api.contract_cached(qasm, meas, ordering, bool(rec["reduce"]))
+    first = time.perf_counter() - t0
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        val, flops, nodes, hit = host_api.contract_cached(qasm, meas, ordering, bool(rec["reduce"]))
+        best = min(best, time.perf_counter() - t0)
+    ok = abs(val - complex(*rec["value"])) <= 1e-10 * max(1.0, abs(complex(*rec["value"])))
+    print(json.dumps({"config": name + " (plan cache)", "matches_reference": bool(ok), "first_call_ms": first * 1e3, "cached_call_ms": best * 1e3,
+                      "cache_hit": bool(hit), "units": flops}))
+
+
 time_network("qft8_X8")
 time_plan_replay("qft8_X8")
 time_plan_replay("ghz1000_zeros")
 time_network("ghz1000_zeros")
 time_network("ghz1000_ones")
+time_cached("ghz1000_zeros")
+time_cached("ghz1000_ones")
+time_cached("qft8_X8")
 time_network("qaoa20_node5_m125")
 time_network("rand20_cn3_d12_zeros")
 time_maxcut("3reg30_p1_default", 300)
