@@ -2,10 +2,13 @@
 // Counterpart of /root/reference/src/maxcut.cpp:227-328, mode 0 (find the QAOA angles that maximise F_p).
 //  * The objective is the reference's F_p (maxcut.cpp:162-204) evaluated by QaoaObjective: per-edge light-cone
 //    networks planned once, all edges of this rank in one grouped launch per evaluation.
-//  * The reference maximises with NLopt's COBYLA (third-party, vendored, no stopping criterion set); NLopt is out of
-//    scope here, so a small derivative-free Nelder-Mead ascent with an evaluation cap takes its place.  Same start
-//    point (beta = 0.392699, gamma = 0.785399, maxcut.cpp:155-157); the angle file is rewritten after every
-//    evaluation like the reference does (maxcut.cpp:199-202).
+//  * The reference maximises with NLopt's COBYLA, no stopping criterion set (maxcut.cpp:211-213).  When the build finds the
+//    NLopt tree the reference vendors (third-party; qtorch_b200/build.py compiles it out of tree into bin/_nlopt), this
+//    front-end does exactly the same -- nlopt::opt(LN_COBYLA, 2p), set_max_objective, optimize from beta = 0.392699,
+//    gamma = 0.785399 (maxcut.cpp:155-157) -- so the sequence of evaluated angles is the reference's (the objective values
+//    agree to ~1e-15) and the angle file holds the last evaluated angles, as the reference leaves it (maxcut.cpp:199-202).
+//    An optional evaluation cap maps to set_maxeval.  Without NLopt (QTB_HAVE_NLOPT undefined) a small Nelder-Mead ascent
+//    with an evaluation cap takes its place and the binary says so.
 //  * Multi-GPU: started once per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment (e.g.
 //    `torchrun --no-python --nproc-per-node N maxcutQAOA ...`), every process owns the edges e with e % WORLD_SIZE == RANK
 //    and the partial objectives meet in one NCCL allreduce per evaluation (device::Job::FromEnvironment).  All ranks
@@ -20,6 +23,9 @@
 
 #include "../host/qtorch.hpp"
 #include "../host/maxcut.h"
+#ifdef QTB_HAVE_NLOPT
+#include <nlopt.hpp>
+#endif
 
 static std::vector<double> nelderMeadMaximise(const std::function<double(const std::vector<double> &)> &f, std::vector<double> x0,
                                               int maxEvals, double step, int &evals) {
@@ -88,7 +94,11 @@ int main(int argc, char *argv[]) {
     }
     if (mode != 0 && mode != 2) { std::cout << "mode must be 0, 1 or 2" << std::endl; return -1; }
     const std::string outputPath(mode == 2 ? "tempAngles.txt" : argv[4]);
+#ifdef QTB_HAVE_NLOPT
+    const int maxEvals = (mode == 0 && argc > 5) ? atoi(argv[5]) : 0;          // 0: no cap, like the reference
+#else
     const int maxEvals = (mode == 0 && argc > 5) ? atoi(argv[5]) : 200;
+#endif
     try {
         Timer clock;
         clock.start();
@@ -117,12 +127,35 @@ int main(int argc, char *argv[]) {
         Timer opt;
         opt.start();
         int evals = 0;
+#ifdef QTB_HAVE_NLOPT
+        // the reference's optimiser call, maxcut.cpp:211-213 (every rank runs the same deterministic COBYLA on the same
+        // allreduced values); nlopt reports "roundoff-limited" by exception once the trust region collapses, as in the reference
+        struct Ctx { decltype(F_p) *f; int *evals; } cctx{&F_p, &evals};
+        nlopt::opt optimization(nlopt::LN_COBYLA, 2 * p);
+        optimization.set_max_objective([](const std::vector<double> &x, std::vector<double> &, void *d) -> double {
+            Ctx *c = static_cast<Ctx *>(d);
+            ++*c->evals;
+            return (*c->f)(x);
+        }, &cctx);
+        if (maxEvals > 0) optimization.set_maxeval(maxEvals);
+        std::vector<double> best = start;
+        try {
+            best = optimization.optimize(start);
+        } catch (std::runtime_error &error) {
+            if (lead) std::cout << error.what() << std::endl;              // e.g. "nlopt roundoff-limited" (maxcut.cpp:217-221)
+        }
+        const double seconds = opt.getElapsed();
+        if (lead) {
+            std::cout << "Optimiser: NLopt LN_COBYLA" << std::endl;
+#else
         const std::vector<double> best = nelderMeadMaximise(F_p, start, maxEvals, 0.1, evals);
         const double seconds = opt.getElapsed();
         if (lead) {
+            std::cout << "Optimiser: Nelder-Mead (built without NLopt; the reference uses COBYLA)" << std::endl;
             std::ofstream angles(outputPath);
             for (double a : best) angles << a << " ";
             angles.close();
+#endif
             std::cout.precision(12);
             std::cout << "F_p(start) evaluations: " << evals << ", best F_p = " << bestSeen << std::endl;
             std::cout.precision(6);

@@ -3,6 +3,8 @@
   qtorch_b200/libqtorch_b200.so   CUDA engine + C ABI (include/qtorch_b200.h), sm_100a only
   qtorch_b200/bin/qtorch          drop-in `qtorch <script.inp>` front-end (host mirror, C++14)
   qtorch_b200/bin/qtb_harness     full-precision driver used by the parity tests
+  qtorch_b200/bin/maxcutQAOA      drop-in `maxcutQAOA <graph> <p> <mode> ...` front-end; links NLopt's COBYLA (bin/_nlopt, built from the
+                                  tree the reference vendors) when that tree is present at build time
 
 `python -m qtorch_b200.build` or `qtorch_b200.build.build_all()`.
 """
@@ -41,8 +43,34 @@ def build_engine(force=False, verbose=False):
     return LIB
 
 
+NLOPT_SRC = os.environ.get("QTB_NLOPT_SRC", "/root/reference/nlopt-2.4.2")
+NLOPT = os.path.join(BIN, "_nlopt")
+
+
+def build_nlopt():
+    """NLopt 2.4.2 -- the third-party optimiser the reference vendors for maxcutQAOA (src/maxcut.cpp:211-213, LN_COBYLA) -- compiled
+    OUT OF TREE from the sources where they lie (nothing of it enters the repository) into bin/_nlopt (static library + headers;
+    git-ignored, travels to the GPU box).  Returns the install prefix, or None when the tree is absent and nothing was built before:
+    maxcutQAOA then falls back to its Nelder-Mead ascent."""
+    lib = os.path.join(NLOPT, "lib", "libnlopt.a")
+    if os.path.exists(lib) and os.path.exists(os.path.join(NLOPT, "include", "nlopt.hpp")):
+        return NLOPT
+    if not os.path.exists(os.path.join(NLOPT_SRC, "configure")):
+        return None
+    import tempfile
+    with tempfile.TemporaryDirectory(prefix="qtb_nlopt_") as d:
+        try:
+            for cmd in ([os.path.join(NLOPT_SRC, "configure"), "--prefix=" + NLOPT, "--disable-shared", "--without-octave", "--without-python",
+                         "--without-guile", "--without-matlab"], ["make", "-j8"], ["make", "install"]):
+                subprocess.run(cmd, cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except (subprocess.CalledProcessError, OSError):
+            return None
+    return NLOPT if os.path.exists(lib) else None
+
+
 def build_host(force=False):
     os.makedirs(BIN, exist_ok=True)
+    nlopt = build_nlopt()
     hdrs = _sources("host", (".h", ".hpp")) + [os.path.join(ROOT, "include", "qtorch_b200.h"), LIB]
     out = []
     for name, src in (("qtb_harness", "qtb_harness.cpp"), ("qtorch", "qtorch_main.cpp"), ("maxcutQAOA", "maxcut_main.cpp")):
@@ -51,6 +79,8 @@ def build_host(force=False):
         if force or _newer(target, hdrs + [source]):
             cmd = ["g++", "-std=c++14", "-O2", "-o", target, source, "-L" + HERE, "-lqtorch_b200",
                    "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
+            if name == "maxcutQAOA" and nlopt:
+                cmd += ["-DQTB_HAVE_NLOPT", "-I" + os.path.join(nlopt, "include"), os.path.join(nlopt, "lib", "libnlopt.a"), "-lm"]
             subprocess.run(cmd, check=True)
         out.append(target)
     target = os.path.join(HERE, "libqtorch_host.so")

@@ -737,6 +737,15 @@ static int launch_generic(qtb_ctx *ctx, const DevStep &st, cudaStream_t s) {
     return QTB_OK;
 }
 
+// ---- debugging aid: per-level clock stamps of compiled micro blobs (QTB_MICRO_TIMELINE=1; qtb_debug_dump_micro_timelines) -------
+struct MicroTimeline { unsigned long long *dev = nullptr; uint32_t nLevels = 0; std::vector<uint32_t> items, maxSerial; };
+static std::vector<MicroTimeline> g_microTimelines;
+static bool micro_timeline_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_MICRO_TIMELINE"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
+
 // ---- micro-batch blob assembly -----------------------------------------------------------------
 // Builds: MicroHeader | levelItemStart | items | steps (copy steps first at level 0) | payload
 static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std::vector<PendingUpload> &ups,
@@ -801,7 +810,21 @@ static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std:
     const size_t payloadOff = off;
     off += payload.size();
     blob.assign(off, 0);
-    MicroHeader hdr{nLevels, nItems, nSteps, (uint32_t)stepsOff, (uint32_t)payloadOff, 0u, 0ull};
+    MicroHeader hdr{nLevels, nItems, nSteps, (uint32_t)stepsOff, (uint32_t)payloadOff, 0u, 0ull, 0ull};
+    if (micro_timeline_enabled() && devBase == nullptr && ups.empty()) {          // compiled plans only (their blobs live as long as the plan)
+        MicroTimeline tl;
+        tl.nLevels = nLevels;
+        if (cudaMalloc((void **)&tl.dev, (size_t)(nLevels + 2) * 8) == cudaSuccess) {
+            cudaMemset(tl.dev, 0, (size_t)(nLevels + 2) * 8);
+            for (uint32_t l = 0; l < nLevels; l++) {
+                uint32_t maxSerial = 0;
+                for (const auto &h : sorted[l]) maxSerial = std::max(maxSerial, h.serial);
+                tl.items.push_back((uint32_t)perLevel[l].size()); tl.maxSerial.push_back(maxSerial);
+            }
+            hdr.timelinePtr = (uint64_t)tl.dev;
+            g_microTimelines.push_back(tl);
+        } else cudaGetLastError();
+    }
     if (prefetchPtr && prefetchBytes) { hdr.prefetchPtr = (uint64_t)prefetchPtr; hdr.prefetchBytes = (uint32_t)std::min<size_t>(prefetchBytes, 8u << 20); }
     else if (!payload.empty() && devBase) { hdr.prefetchPtr = (uint64_t)(devBase + payloadOff); hdr.prefetchBytes = (uint32_t)payload.size(); }
     memcpy(blob.data(), &hdr, sizeof(hdr));
@@ -1255,6 +1278,21 @@ int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos
     }
     c->hasData = true;
     return QTB_OK;
+}
+
+// debugging aid (not part of the public header): prints the clock stamps the grouped launches of compiled plans left behind
+int qtb_debug_dump_micro_timelines(int maxBlobs) {
+    cudaDeviceSynchronize();
+    int n = 0;
+    for (const MicroTimeline &tl : g_microTimelines) {
+        if (n++ >= maxBlobs) break;
+        std::vector<unsigned long long> h(tl.nLevels + 2);
+        if (cudaMemcpy(h.data(), tl.dev, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); continue; }
+        fprintf(stderr, "micro blob %d: %u levels, %llu cycles\n", n - 1, tl.nLevels, h[tl.nLevels] - h[0]);
+        for (uint32_t l = 0; l < tl.nLevels; l++)
+            fprintf(stderr, "  level %3u: %8llu cycles  %4u items  max serial %5u MACs\n", l, h[l + 1] - h[l], tl.items[l], tl.maxSerial[l]);
+    }
+    return n;
 }
 
 // ---- stats / trace ------------------------------------------------------------------------------

@@ -119,6 +119,7 @@ struct MicroHeader {
     uint32_t controlBytes;        // header + level table + items + steps (what the kernel stages in shared memory)
     uint32_t prefetchBytes;       // size of the operand region to pull into L2 up front (0 = none)
     uint64_t prefetchPtr;         // device address of that region (plan input blob / upload payload)
+    uint64_t timelinePtr;         // debugging (QTB_MICRO_TIMELINE=1): device array of nLevels + 2 clock64() stamps, else 0
 };
 struct MicroItem { uint32_t step; uint32_t chunk; };      // chunk: bits 0-23 index of the item inside its step, bits 24-28 log2 of the lanes per output, bits 29-30 log2 of the passes
 
@@ -156,6 +157,8 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + off));
     }
     __syncthreads();
+    unsigned long long *timeline = reinterpret_cast<unsigned long long *>(hdr.timelinePtr);
+    if (timeline && threadIdx.x == 0) timeline[0] = clock64();
     const uint8_t *cb = staged ? ctrl : blob;
     const uint32_t *lis = reinterpret_cast<const uint32_t *>(cb + sizeof(MicroHeader));
     const MicroItem *items = reinterpret_cast<const MicroItem *>(lis + hdr.nLevels + 1);
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
             }
         }
         __syncthreads();
+        if (timeline && threadIdx.x == 0) timeline[lvl + 1] = clock64();
     }
 }
 

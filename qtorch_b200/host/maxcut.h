@@ -303,6 +303,13 @@ private:
                     lg.runMinFill();
                     lg.LGContract();
                 }
+                if (std::getenv("QTB_QAOA_VERBOSE")) {
+                    std::vector<int> lv(net->GetNumOriginalNodes(), 0);
+                    int depth = 0;
+                    for (const auto &r : net->GetPlan()) { const int l = 1 + std::max(lv[r.a], lv[r.b]); lv.push_back(l); depth = std::max(depth, l); }
+                    std::cerr << "edge " << edge << " attempt " << attempt << (attempt < planTries ? " stochastic" : " minfill") << ": steps " << net->GetPlan().size()
+                              << " levels " << depth << " units " << net->getNumFloatOps() << std::endl;
+                }
                 if (!best || net->getNumFloatOps() < best->getNumFloatOps()) best = net;
             }
         } catch (...) {
