@@ -443,7 +443,7 @@ def main():
 
     maxcut = {"metric": "maxcut_zz_terms_per_s", "unit": "terms/s", "scaling": "strong",
               "workload": "cfg3: 3regRand30Node50.dgf (30 vertices, 45 edges) objective F_p through QaoaObjective (host/maxcut.h): edges dealt "
-                          "round-robin over %d rank(s), one CUDA graph (2p gate tables H2D, scatter, one CTA per edge, gather) and one in-stream "
+                          "round-robin over %d rank(s), one CUDA graph (2p gate tables H2D, scatter, one CTA -- for p=2 one thread-block cluster -- per edge, gather) and one in-stream "
                           "NCCL allreduce per evaluation; evaluations are sequential like the optimiser's" % world,
               "p1": maxcut_run("3reg30_p1_default", 300), "p2": maxcut_run("3reg30_p2_default", 200)}
     maxcut["value"] = maxcut["p1"]["terms_per_s"]

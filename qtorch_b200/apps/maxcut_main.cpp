@@ -7,7 +7,8 @@
 //    front-end does exactly the same -- nlopt::opt(LN_COBYLA, 2p), set_max_objective, optimize from beta = 0.392699,
 //    gamma = 0.785399 (maxcut.cpp:155-157) -- so the sequence of evaluated angles is the reference's (the objective values
 //    agree to ~1e-15) and the angle file holds the last evaluated angles, as the reference leaves it (maxcut.cpp:199-202).
-//    An optional evaluation cap maps to set_maxeval.  Without NLopt (QTB_HAVE_NLOPT undefined) a small Nelder-Mead ascent
+//    The reference is stopped by NLopt's round-off detection, which only its numerical noise triggers; here xtol_abs = 1e-9 ends
+//    the run instead (plus an evaluation cap, optional argument, default 20000).  Without NLopt (QTB_HAVE_NLOPT undefined) a small Nelder-Mead ascent
 //    with an evaluation cap takes its place and the binary says so.
 //  * Multi-GPU: started once per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment (e.g.
 //    `torchrun --no-python --nproc-per-node N maxcutQAOA ...`), every process owns the edges e with e % WORLD_SIZE == RANK
@@ -137,7 +138,11 @@ int main(int argc, char *argv[]) {
             ++*c->evals;
             return (*c->f)(x);
         }, &cctx);
-        if (maxEvals > 0) optimization.set_maxeval(maxEvals);
+        // The reference sets no stopping criterion: its runs end when NLopt detects round-off ("nlopt roundoff-limited"), which the
+        // run-to-run noise of its randomly ordered contractions triggers after a few hundred evaluations.  This objective is
+        // deterministic, so that never happens: stop where the reference's 6-digit angle file can no longer change.
+        optimization.set_xtol_abs(1e-9);
+        optimization.set_maxeval(maxEvals > 0 ? maxEvals : 20000);
         std::vector<double> best = start;
         try {
             best = optimization.optimize(start);

@@ -84,8 +84,7 @@ static int batch_enqueue(qtb_ctx *ctx, qtb_batch *b, bool withReadback) {
     }
     const int n = (int)b->plans.size();
     if (b->allMicro) {
-        k_micro<<<n, QTB_MICRO_THREADS, QTB_MICRO_SMEM, s>>>(nullptr, b->blobAddrDev);
-        CU(cudaGetLastError());
+        ST(launch_micro_plans(ctx, n, b->units, b->blobAddrDev, s));
     } else {
         const int nAux = std::min(n, 16);
         while ((int)ctx->auxStreams.size() < nAux) {

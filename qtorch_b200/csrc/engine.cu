@@ -980,6 +980,51 @@ static int enqueue_big(qtb_ctx *ctx, const StepGeom &g, int kind, const GettChoi
     return launch_generic(ctx, st, s);
 }
 
+// n independent all-micro plans in ONE launch (k_micro_batch: 512 threads): one CTA per plan, or -- when the plans are heavy and there are SMs
+// to spare -- one thread-block cluster per plan (kernels.cuh: the CTAs of a cluster share every level's items).  The cluster size is
+// the largest c <= 8 for which all n clusters are resident at once (cudaOccupancyMaxActiveClusters: one CTA per SM, a cluster has to
+// fit one GPC).  Light plans stay on one CTA: a cluster barrier per level costs more than it buys (p=1 QAOA terms, 27 000 units each:
+// 0.072 ms per evaluation on one CTA per term, 0.076 ms on clusters of three).  QTB_MICRO_CLUSTER=c forces a size, 1 turns clusters off.
+static const long long MICRO_CLUSTER_MIN_UNITS = 100000;
+static int micro_cluster_size(qtb_ctx *ctx, int n, long long unitsPerPlan) {
+    static int forced = -2;
+    if (forced == -2) { const char *e = getenv("QTB_MICRO_CLUSTER"); forced = e ? std::max(1, std::min(8, atoi(e))) : -1; }
+    if (forced > 0) return forced;
+    if (unitsPerPlan < MICRO_CLUSTER_MIN_UNITS) return 1;
+    static std::mutex mu;
+    static std::unordered_map<long long, int> cache;                   // (device, n) -> size
+    std::lock_guard<std::mutex> lk(mu);
+    const long long key = ((long long)ctx->device << 32) | (unsigned)n;
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int best = 1;
+    for (int c = std::min(8, ctx->numSMs / std::max(1, n)); c >= 2; c--) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n * c)); cfg.blockDim = dim3(QTB_MICRO_THREADS_BATCH); cfg.dynamicSmemBytes = QTB_MICRO_SMEM_FOR(QTB_MICRO_THREADS_BATCH);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = (unsigned)c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int active = 0;
+        if (cudaOccupancyMaxActiveClusters(&active, k_micro_batch, &cfg) == cudaSuccess && active >= n) { best = c; break; }
+        cudaGetLastError();
+    }
+    cache[key] = best;
+    return best;
+}
+static int launch_micro_plans(qtb_ctx *ctx, int n, long long unitsTotal, const uint64_t *blobAddrDev, cudaStream_t s) {
+    const int c = micro_cluster_size(ctx, n, unitsTotal / std::max(1, n));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n * c)); cfg.blockDim = dim3(QTB_MICRO_THREADS_BATCH); cfg.dynamicSmemBytes = QTB_MICRO_SMEM_FOR(QTB_MICRO_THREADS_BATCH); cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = c > 1 ? 1 : 0;
+    const uint8_t *nullBase = nullptr;
+    CU(cudaLaunchKernelEx(&cfg, k_micro_batch, nullBase, blobAddrDev));
+    return QTB_OK;
+}
+
 // ================================================================================================
 // C ABI
 extern "C" {
@@ -1026,6 +1071,7 @@ static int ctx_init(qtb_ctx *ctx, int device) {
     CU(cudaMemset(ctx->zeroOffsetDev, 0, 8));
     CU(cudaEventCreateWithFlags(&ctx->ringEvent, cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_micro, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QTB_MICRO_SMEM));
+    CU(cudaFuncSetAttribute(k_micro_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QTB_MICRO_SMEM_FOR(QTB_MICRO_THREADS_BATCH)));
     for (auto &inst : g_gett) {
         CU(cudaFuncSetAttribute(inst.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inst.smem));
         int occ = 1;

@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) k_step_warp(const DevStep st) {
 // QTB_MICRO_CHUNK outputs which the CTA's warps share; __syncthreads() separates levels (it also
 // orders the global-memory writes of one level before the reads of the next, CTA scope).
 #define QTB_MICRO_CHUNK 128
-#define QTB_MICRO_THREADS 1024
+#define QTB_MICRO_THREADS 1024         // single plans (latency-bound chains of tiny steps: GHZ-1000 is 2 999 levels of one item)
+#define QTB_MICRO_THREADS_BATCH 512    // term batches: 16 warps x 128 registers, a lane keeps 16 operand loads in flight; measured with clusters: p=2 objective 0.257 ms (1024) -> 0.198 ms (512)
 
 struct MicroHeader {
     uint32_t nLevels, nItems, nSteps, stepsOffset;
@@ -132,19 +133,28 @@ struct MicroWarpScratch {
 };
 static_assert(sizeof(DevStep) % 4 == 0, "DevStep is copied word-wise");
 #define QTB_MICRO_CTRL_BYTES (96 * 1024)       // control structures up to this size are staged in shared memory
-#define QTB_MICRO_SMEM ((QTB_MICRO_THREADS / 32) * sizeof(MicroWarpScratch) + QTB_MICRO_CTRL_BYTES)
+#define QTB_MICRO_SMEM_FOR(T) (((T) / 32) * sizeof(MicroWarpScratch) + QTB_MICRO_CTRL_BYTES)
+#define QTB_MICRO_SMEM QTB_MICRO_SMEM_FOR(QTB_MICRO_THREADS)
 
-__global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *__restrict__ blobBase,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_micro_t(const uint8_t *__restrict__ blobBase,
                                                                   const uint64_t *__restrict__ blobOffsets) {
     extern __shared__ __align__(16) uint8_t microSmem[];
-    const uint8_t *blob = blobBase + blobOffsets[blockIdx.x];
+    // A plan may be run by a thread-block CLUSTER (launch attribute; 1 x 1 x 1 when launched plainly): the CTAs of a cluster share
+    // the items of every level -- a level of a QAOA p=2 term is bound by one SM's load/store unit (scattered 16-byte operand reads:
+    // 780 cycles per multiply-add and warp, tools/micro_timeline.py), which more SMs multiply -- and meet in a cluster barrier
+    // between levels (release / acquire at cluster scope orders the global-memory writes of a level before the next level's reads).
+    uint32_t crank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    const uint8_t *blob = blobBase + blobOffsets[blockIdx.x / csize];
     const MicroHeader hdr = *reinterpret_cast<const MicroHeader *>(blob);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     MicroWarpScratch &ws = reinterpret_cast<MicroWarpScratch *>(microSmem)[warp];
     // A launch usually starts cold (the big steps in between stream gigabytes through L2), and every item would
     // otherwise chase item -> descriptor -> operand through DRAM one round trip at a time: stage the control
     // structures in shared memory with one cooperative read and pull the operand region into L2 meanwhile.
-    uint8_t *ctrl = microSmem + (QTB_MICRO_THREADS / 32) * sizeof(MicroWarpScratch);
+    uint8_t *ctrl = microSmem + (THREADS / 32) * sizeof(MicroWarpScratch);
     const bool staged = hdr.controlBytes <= QTB_MICRO_CTRL_BYTES;
     if (staged) {
         const uint4 *src = reinterpret_cast<const uint4 *>(blob);
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
     }
     __syncthreads();
     unsigned long long *timeline = reinterpret_cast<unsigned long long *>(hdr.timelinePtr);
-    if (timeline && threadIdx.x == 0) timeline[0] = clock64();
+    if (timeline && threadIdx.x == 0 && crank == 0) timeline[0] = clock64();
     const uint8_t *cb = staged ? ctrl : blob;
     const uint32_t *lis = reinterpret_cast<const uint32_t *>(cb + sizeof(MicroHeader));
     const MicroItem *items = reinterpret_cast<const MicroItem *>(lis + hdr.nLevels + 1);
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
 
     for (uint32_t lvl = 0; lvl < hdr.nLevels; lvl++) {
         const uint32_t i0 = lis[lvl], i1 = lis[lvl + 1];
-        for (uint32_t it = i0 + warp; it < i1; it += nw) {
+        for (uint32_t it = i0 + crank * nw + warp; it < i1; it += nw * csize) {
             const MicroItem item = items[it];
             // descriptor -> this warp's shared-memory slot (one coalesced read)
             __syncwarp();
@@ -218,10 +228,41 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
                     free_offsets(st, c, ba, bb);
                     const double2 *pa = A + ba, *pb = B + bb;
                     if (tabled) {
-#pragma unroll 4
-                        for (uint32_t s = sg; s < K; s += G) cmac(cr, ci, pa[ws.sumA[s]], pb[ws.sumB[s]]);
+                        // a step's time is its serial chain of memory round trips (tools/micro_timeline.py: 450-800 cycles per
+                        // multiply-add when ptxas re-used the load registers): eight terms per round -- sixteen loads in flight --
+                        // then four, then the rest
+                        uint32_t s = sg;
+                        for (; s + 7 * G < K; s += 8 * G) {
+                            double2 va[8], vb[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { va[u] = pa[ws.sumA[s + u * G]]; vb[u] = pb[ws.sumB[s + u * G]]; }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) cmac(cr, ci, va[u], vb[u]);
+                        }
+                        for (; s + 3 * G < K; s += 4 * G) {
+                            double2 va[4], vb[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { va[u] = pa[ws.sumA[s + u * G]]; vb[u] = pb[ws.sumB[s + u * G]]; }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) cmac(cr, ci, va[u], vb[u]);
+                        }
+                        for (; s < K; s += G) cmac(cr, ci, pa[ws.sumA[s]], pb[ws.sumB[s]]);
                     } else {
-                        for (uint32_t s = sg; s < K; s += G) {
+                        // long sums (K > QTB_MICRO_TAB, e.g. the inner product that closes a term): four terms per round --
+                        // offsets first, then all eight loads, then the FMAs -- so a lane has eight loads in flight instead
+                        // of paying one memory round trip per term (measured 770 cycles per term before)
+                        uint32_t s = sg;
+                        for (; s + 3 * G < K; s += 4 * G) {
+                            uint64_t oa[4], ob[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) sum_offsets(st, s + u * G, oa[u], ob[u]);
+                            double2 va[4], vb[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { va[u] = pa[oa[u]]; vb[u] = pb[ob[u]]; }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) cmac(cr, ci, va[u], vb[u]);
+                        }
+                        for (; s < K; s += G) {
                             uint64_t oa, ob;
                             sum_offsets(st, s, oa, ob);
                             cmac(cr, ci, pa[oa], pb[ob]);
@@ -235,9 +276,17 @@ __global__ void __launch_bounds__(QTB_MICRO_THREADS, 1) k_micro(const uint8_t *_
                 if (c < NC && sg == 0) st.C[c] = make_double2(cr, ci);
             }
         }
-        __syncthreads();
-        if (timeline && threadIdx.x == 0) timeline[lvl + 1] = clock64();
+        if (csize > 1) {
+            __threadfence();
+            asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+        } else {
+            __syncthreads();
+        }
+        if (timeline && threadIdx.x == 0 && crank == 0) timeline[lvl + 1] = clock64();
     }
 }
+
+static constexpr auto k_micro = k_micro_t<QTB_MICRO_THREADS>;                 // single plans / eager groups
+static constexpr auto k_micro_batch = k_micro_t<QTB_MICRO_THREADS_BATCH>;     // term batches (launch_micro_plans)
 
 }  // namespace qtb

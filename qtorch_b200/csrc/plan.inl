@@ -498,7 +498,9 @@ int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const dou
         uint64_t *addr = reinterpret_cast<uint64_t *>(ctx->ringHost + off);
         for (int i = 0; i < n; i++) addr[i] = reinterpret_cast<uint64_t>(plans[i]->microBlobDev);
         CU(cudaMemcpyAsync(ctx->ringDev + off, ctx->ringHost + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        k_micro<<<n, QTB_MICRO_THREADS, QTB_MICRO_SMEM, ctx->stream>>>(nullptr, reinterpret_cast<const uint64_t *>(ctx->ringDev + off));
+        long long unitsTotal = 0;
+        for (int i = 0; i < n; i++) unitsTotal += plans[i]->units;
+        ST(launch_micro_plans(ctx, n, unitsTotal, reinterpret_cast<const uint64_t *>(ctx->ringDev + off), ctx->stream));
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ringEvent, ctx->stream));
         ctx->ringEventValid = true;

@@ -98,7 +98,7 @@ def test_maxcut_cli_follows_the_reference_cobyla_trajectory(built, tmp_path, cas
     work = os.path.join(str(tmp_path), "c")
     os.makedirs(work)
     r = subprocess.run([exe, os.path.join(GOLDEN, rec["graph"]), str(rec["p"]), "0", "angles.txt"], cwd=work, capture_output=True, text=True,
-                       timeout=900, env=dict(os.environ, QTORCH_QUIET="1"))
+                       timeout=120, env=dict(os.environ, QTORCH_QUIET="1"))
     assert r.returncode == 0 and "Optimiser: NLopt LN_COBYLA" in r.stdout, r.stdout[-1500:]
     evals = int([l for l in r.stdout.splitlines() if "evaluations:" in l][0].split("evaluations:")[1].split(",")[0])
     angles = [float(x) for x in open(os.path.join(work, "angles.txt")).read().split()]
