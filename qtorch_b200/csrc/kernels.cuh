@@ -202,15 +202,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_micro_t(const uint8_t *__restric
                 }
                 continue;
             }
-            const bool tabled = K <= QTB_MICRO_TAB;
-            if (tabled) {
-                for (uint32_t s = lane; s < K; s += 32) {
-                    uint64_t oa, ob;
-                    sum_offsets(st, s, oa, ob);
-                    ws.sumA[s] = (uint32_t)oa; ws.sumB[s] = (uint32_t)ob;
-                }
-                __syncwarp();
+            // offsets of the summed terms: a table for the low four summed digits (all of them when K <= 256); a longer sum walks
+            // it once per block of 256 terms, adding the block's own offset (digit contributions are additive)
+            const uint32_t KT = K < QTB_MICRO_TAB ? K : QTB_MICRO_TAB;
+            for (uint32_t s = lane; s < KT; s += 32) {
+                uint64_t oa, ob;
+                sum_offsets(st, s, oa, ob);
+                ws.sumA[s] = (uint32_t)oa; ws.sumB[s] = (uint32_t)ob;
             }
+            __syncwarp();
             // lane layout (chosen by the host, build_micro_blob): G = 2^lg lanes cover one output along the summed index and a
             // shuffle tree adds their slices; P = 32 / G outputs per pass, 2^lp <= 4 passes per item.  Tiny results (NC < 32) and
             // steps with few outputs but long sums use the whole warp -- and more warps of the CTA -- this way.  The summed loop
@@ -227,46 +227,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_micro_t(const uint8_t *__restric
                     uint64_t ba, bb;
                     free_offsets(st, c, ba, bb);
                     const double2 *pa = A + ba, *pb = B + bb;
-                    if (tabled) {
-                        // a step's time is its serial chain of memory round trips (tools/micro_timeline.py: 450-800 cycles per
-                        // multiply-add when ptxas re-used the load registers): eight terms per round -- sixteen loads in flight --
-                        // then four, then the rest
+                    // a step's time is its serial chain of memory round trips (tools/micro_timeline.py: 450-800 cycles per
+                    // multiply-add when ptxas re-used the load registers, 770 when every term's offsets were rebuilt digit by
+                    // digit): eight terms per round -- sixteen loads in flight -- then four, then the rest
+                    for (uint32_t hi = 0; hi < K; hi += QTB_MICRO_TAB) {
+                        const double2 *pah = pa, *pbh = pb;
+                        if (K > QTB_MICRO_TAB) {
+                            uint64_t oaH, obH;
+                            sum_offsets(st, hi, oaH, obH);
+                            pah += oaH; pbh += obH;
+                        }
                         uint32_t s = sg;
-                        for (; s + 7 * G < K; s += 8 * G) {
+                        for (; s + 7 * G < KT; s += 8 * G) {
                             double2 va[8], vb[8];
 #pragma unroll
-                            for (int u = 0; u < 8; u++) { va[u] = pa[ws.sumA[s + u * G]]; vb[u] = pb[ws.sumB[s + u * G]]; }
+                            for (int u = 0; u < 8; u++) { va[u] = pah[ws.sumA[s + u * G]]; vb[u] = pbh[ws.sumB[s + u * G]]; }
 #pragma unroll
                             for (int u = 0; u < 8; u++) cmac(cr, ci, va[u], vb[u]);
                         }
-                        for (; s + 3 * G < K; s += 4 * G) {
+                        for (; s + 3 * G < KT; s += 4 * G) {
                             double2 va[4], vb[4];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) { va[u] = pa[ws.sumA[s + u * G]]; vb[u] = pb[ws.sumB[s + u * G]]; }
+                            for (int u = 0; u < 4; u++) { va[u] = pah[ws.sumA[s + u * G]]; vb[u] = pbh[ws.sumB[s + u * G]]; }
 #pragma unroll
                             for (int u = 0; u < 4; u++) cmac(cr, ci, va[u], vb[u]);
                         }
-                        for (; s < K; s += G) cmac(cr, ci, pa[ws.sumA[s]], pb[ws.sumB[s]]);
-                    } else {
-                        // long sums (K > QTB_MICRO_TAB, e.g. the inner product that closes a term): four terms per round --
-                        // offsets first, then all eight loads, then the FMAs -- so a lane has eight loads in flight instead
-                        // of paying one memory round trip per term (measured 770 cycles per term before)
-                        uint32_t s = sg;
-                        for (; s + 3 * G < K; s += 4 * G) {
-                            uint64_t oa[4], ob[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) sum_offsets(st, s + u * G, oa[u], ob[u]);
-                            double2 va[4], vb[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) { va[u] = pa[oa[u]]; vb[u] = pb[ob[u]]; }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) cmac(cr, ci, va[u], vb[u]);
-                        }
-                        for (; s < K; s += G) {
-                            uint64_t oa, ob;
-                            sum_offsets(st, s, oa, ob);
-                            cmac(cr, ci, pa[oa], pb[ob]);
-                        }
+                        for (; s < KT; s += G) cmac(cr, ci, pah[ws.sumA[s]], pbh[ws.sumB[s]]);
                     }
                 }
                 for (uint32_t off = P; off < 32; off <<= 1) {            // no-op when G = 1
