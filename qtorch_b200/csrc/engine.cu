@@ -746,6 +746,8 @@ static bool micro_timeline_enabled() {
     return v == 1;
 }
 
+static int launch_micro_group(qtb_ctx *ctx, const uint8_t *blobBase, const uint64_t *offsetDev, long long units, cudaStream_t s);
+
 // ---- micro-batch blob assembly -----------------------------------------------------------------
 // Builds: MicroHeader | levelItemStart | items | steps (copy steps first at level 0) | payload
 static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std::vector<PendingUpload> &ups,
@@ -893,8 +895,9 @@ static int flush_locked(qtb_ctx *ctx) {
     if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, ctx->stream)); }
     CU(cudaMemcpyAsync(ctx->ringDev + off, ctx->ringHost + off, blob.size(), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.bytes_h2d += (long long)blob.size();
-    k_micro<<<1, QTB_MICRO_THREADS, QTB_MICRO_SMEM, ctx->stream>>>(ctx->ringDev + off, ctx->zeroOffsetDev);
-    CU(cudaGetLastError());
+    long long groupUnits = 0;
+    for (const auto &ps : ctx->pending) groupUnits += 1ll << (2 * (ps.st.rC + ps.st.k));
+    ST(launch_micro_group(ctx, ctx->ringDev + off, ctx->zeroOffsetDev, groupUnits, ctx->stream));
     CU(cudaEventRecord(ctx->ringEvent, ctx->stream));
     ctx->ringEventValid = true;
     if (ctx->trace) { CU(cudaEventRecord(e1, ctx->stream)); ctx->traceRecs.push_back({e0, e1, 0, 0, (int)ctx->pending.size(), KIND_MICRO}); }
@@ -1012,7 +1015,7 @@ static int micro_cluster_size(qtb_ctx *ctx, int n, long long unitsPerPlan) {
     cache[key] = best;
     return best;
 }
-static int launch_micro_plans(qtb_ctx *ctx, int n, long long unitsTotal, const uint64_t *blobAddrDev, cudaStream_t s) {
+static int launch_micro_plans(qtb_ctx *ctx, int n, long long unitsTotal, const uint64_t *blobAddrDev, cudaStream_t s, const uint8_t *blobBase = nullptr) {
     const int c = micro_cluster_size(ctx, n, unitsTotal / std::max(1, n));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n * c)); cfg.blockDim = dim3(QTB_MICRO_THREADS_BATCH); cfg.dynamicSmemBytes = QTB_MICRO_SMEM_FOR(QTB_MICRO_THREADS_BATCH); cfg.stream = s;
@@ -1020,8 +1023,16 @@ static int launch_micro_plans(qtb_ctx *ctx, int n, long long unitsTotal, const u
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = (unsigned)c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = c > 1 ? 1 : 0;
-    const uint8_t *nullBase = nullptr;
-    CU(cudaLaunchKernelEx(&cfg, k_micro_batch, nullBase, blobAddrDev));
+    CU(cudaLaunchKernelEx(&cfg, k_micro_batch, blobBase, blobAddrDev));
+    return QTB_OK;
+}
+// one grouped launch of a single plan segment / eager group: a long chain of tiny steps stays on one CTA of 1024 threads (GHZ-1000:
+// 2 999 levels of one item, a cluster barrier per level would triple its time); a heavy group -- the 273 micro-steps of a config-2
+// term are 1.2e6 units -- takes the batch kernel on a cluster
+static int launch_micro_group(qtb_ctx *ctx, const uint8_t *blobBase, const uint64_t *offsetDev, long long units, cudaStream_t s) {
+    if (units >= 4 * MICRO_CLUSTER_MIN_UNITS && micro_cluster_size(ctx, 1, units) > 1) return launch_micro_plans(ctx, 1, units, offsetDev, s, blobBase);
+    k_micro<<<1, QTB_MICRO_THREADS, QTB_MICRO_SMEM, s>>>(blobBase, offsetDev);
+    CU(cudaGetLastError());
     return QTB_OK;
 }
 

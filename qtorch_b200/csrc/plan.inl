@@ -12,6 +12,7 @@ struct PlanSeg {
     StepGeom g2; bool tIsA = false; const double2 *D = nullptr;
     bool micro = false;
     uint32_t microIndex = 0;      // index into segOffsetsDev
+    long long microUnits = 0;     // sum 4^(rC+k) over the segment's steps (heavy segments run on a cluster, engine.cu launch_micro_group)
     int nSteps = 0;
     StepGeom g; int kind = 0; GettChoice gc{0, false};
     const double2 *A = nullptr, *B = nullptr; double2 *C = nullptr;
@@ -64,8 +65,7 @@ static int plan_enqueue(qtb_ctx *ctx, qtb_plan *pl, cudaStream_t s, size_t segBe
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->trace) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventRecord(e0, s)); }
         if (sg.micro) {
-            k_micro<<<1, QTB_MICRO_THREADS, QTB_MICRO_SMEM, s>>>(pl->microBlobDev, pl->segOffsetsDev + sg.microIndex);
-            CU(cudaGetLastError());
+            ST(launch_micro_group(ctx, pl->microBlobDev, pl->segOffsetsDev + sg.microIndex, sg.microUnits, s));
             ctx->stats.launches++;
         } else if (sg.fused) {
             ST(enqueue_fused(ctx, sg.g, sg.gc, sg.A, sg.B, sg.g2, sg.tIsA, sg.D, sg.C, s));
@@ -153,6 +153,7 @@ static int plan_create_replica(qtb_ctx *ctx, int nInputs, const int *inputRanks,
     auto closeMicro = [&]() {
         if (cur.empty()) return;
         PlanSeg sg; sg.micro = true; sg.microIndex = (uint32_t)microBlobs.size(); sg.nSteps = (int)cur.size();
+        for (const auto &ps : cur) sg.microUnits += 1ll << (2 * (ps.st.rC + ps.st.k));
         pl->segs.push_back(sg);
         microBlobs.emplace_back();                   // assembled once all device addresses are known (below)
         // keep the raw steps: stash them in the blob vector as bytes for now
