@@ -681,12 +681,29 @@ static int launch_apply(qtb_ctx *ctx, const StepGeom &g, bool swap, const double
     return QTB_OK;
 }
 
+// QTB_PDL=1: k_gett launches carry the programmatic-dependent-launch attribute (gett.cuh: griddepcontrol), so the next tile-kernel
+// launch builds its tables on the SMs the previous one has left.  Measured neutral on config 2 (14.589 vs 14.585 ms per term) and
+// slightly negative with two plan lanes competing for SMs (sliced config-2 term 14.45 -> 14.67 ms), so it is off by default.
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QTB_PDL"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
+static int launch_gett_kernel(const GettInst &inst, unsigned grid, const GettParams &p, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)inst.NT); cfg.dynamicSmemBytes = inst.smem; cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, inst.fn, p));
+    return QTB_OK;
+}
 static int launch_gett(qtb_ctx *ctx, const GettParams &p, int cfg, cudaStream_t s) {
     const GettInst &inst = g_gett[cfg];
     const unsigned nTiles = p.nTilesX * p.nTilesY;
     const unsigned grid = std::min<unsigned>(nTiles, (unsigned)(ctx->numSMs * inst.occ));
-    inst.fn<<<grid, inst.NT, inst.smem, s>>>(p);
-    CU(cudaGetLastError());
+    ST(launch_gett_kernel(inst, grid, p, s));
     ctx->stats.launches++;
     return QTB_OK;
 }
@@ -948,7 +965,7 @@ static int enqueue_fused(qtb_ctx *ctx, const StepGeom &g1, const GettChoice &gc1
     add_fusion(g2, tIsA, D, ctx->partials(), inst, p);
     const unsigned nTiles = p.nTilesX * p.nTilesY;
     const unsigned grid = std::min<unsigned>(nTiles, (unsigned)(ctx->numSMs * inst.occ));
-    inst.fn<<<grid, inst.NT, inst.smem, s>>>(p);
+    ST(launch_gett_kernel(inst, grid, p, s));
     k_reduce_final<1><<<1, 32, 0, s>>>(ctx->partials(), out, grid);
     CU(cudaGetLastError());
     ctx->stats.launches += 2;

@@ -177,6 +177,12 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nyValid = p.nyValid;
 
+    // Programmatic dependent launch (opt-in, QTB_PDL=1: the host then sets cudaLaunchAttributeProgrammaticStreamSerialization; both
+    // instructions are no-ops otherwise): the
+    // NEXT tile-kernel launch of the stream may start its CTAs on every SM this grid has left and build its tables while this grid's
+    // last tiles run; it waits (griddepcontrol.wait below) for this grid to complete before it touches global memory.
+    asm volatile("griddepcontrol.launch_dependents;");
+
     // ---- one-time tables: tile-local coordinate -> element offset
     for (int i = tid; i < TM; i += NT) {
         tXx[i] = scatter_bits(i, p.shXx, 0, TMB);
@@ -205,8 +211,8 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         for (int i = tid; i < TM; i += NT) tDx[i] = scatter_bits(i, p.shDx, 0, TMB);
         for (int i = tid; i < TN; i += NT) tDy[i] = (uint32_t)i < nyValid ? scatter_bits(i, p.shDy, 0, p.nyBits) : 0u;
     }
-    // zero the operand ring once: padded y columns (N < TN) are never written again
-    for (int i = tid; i < STAGES * Cfg::STAGE_ELEMS; i += NT) stages[i] = make_double2(0.0, 0.0);
+    // zero the operand ring once when the tile has padded y columns (N < TN): they are never written again
+    if (nyValid < (uint32_t)TN) for (int i = tid; i < STAGES * Cfg::STAGE_ELEMS; i += NT) stages[i] = make_double2(0.0, 0.0);
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(barBase + 8 * s, Cfg::NPT); mbar_init(barBase + 8 * (STAGES + s), NW); }
     }
@@ -245,6 +251,9 @@ __global__ void __launch_bounds__(WX *WY * 32 + 128, 1) k_gett(const GettParams 
         }
     }
     __syncthreads();
+
+    // everything above touched parameters and shared memory only; operands and C belong to the grids before this one
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t smemBase = (uint32_t)__cvta_generic_to_shared(stages);
     const uint32_t nTiles = p.nTilesX * p.nTilesY, nChunks = p.nChunks;
