@@ -1006,9 +1006,13 @@ static int enqueue_big(qtb_ctx *ctx, const StepGeom &g, int kind, const GettChoi
 // fit one GPC).  Light plans stay on one CTA: a cluster barrier per level costs more than it buys (p=1 QAOA terms, 27 000 units each:
 // 0.072 ms per evaluation on one CTA per term, 0.076 ms on clusters of three).  QTB_MICRO_CLUSTER=c forces a size, 1 turns clusters off.
 static const long long MICRO_CLUSTER_MIN_UNITS = 100000;
-static int micro_cluster_size(qtb_ctx *ctx, int n, long long unitsPerPlan) {
+static int micro_cluster_forced() {
     static int forced = -2;
     if (forced == -2) { const char *e = getenv("QTB_MICRO_CLUSTER"); forced = e ? std::max(1, std::min(8, atoi(e))) : -1; }
+    return forced;
+}
+static int micro_cluster_size(qtb_ctx *ctx, int n, long long unitsPerPlan) {
+    const int forced = micro_cluster_forced();
     if (forced > 0) return forced;
     if (unitsPerPlan < MICRO_CLUSTER_MIN_UNITS) return 1;
     static std::mutex mu;
@@ -1047,7 +1051,8 @@ static int launch_micro_plans(qtb_ctx *ctx, int n, long long unitsTotal, const u
 // 2 999 levels of one item, a cluster barrier per level would triple its time); a heavy group -- the 273 micro-steps of a config-2
 // term are 1.2e6 units -- takes the batch kernel on a cluster
 static int launch_micro_group(qtb_ctx *ctx, const uint8_t *blobBase, const uint64_t *offsetDev, long long units, cudaStream_t s) {
-    if (units >= 4 * MICRO_CLUSTER_MIN_UNITS && micro_cluster_size(ctx, 1, units) > 1) return launch_micro_plans(ctx, 1, units, offsetDev, s, blobBase);
+    if ((micro_cluster_forced() > 1 || units >= 4 * MICRO_CLUSTER_MIN_UNITS) && micro_cluster_size(ctx, 1, units) > 1)
+        return launch_micro_plans(ctx, 1, units, offsetDev, s, blobBase);
     k_micro<<<1, QTB_MICRO_THREADS, QTB_MICRO_SMEM, s>>>(blobBase, offsetDev);
     CU(cudaGetLastError());
     return QTB_OK;

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, golden_paths, plan_file
+from conftest import GOLDEN, ROOT, golden_paths, plan_file
 import qtorch_b200 as qt
 from oracle import oracle as O
 
@@ -215,3 +215,15 @@ def test_plan_cache_replays_one_compiled_plan_for_many_measurements(built, netwo
     for rec in (z, o, z):
         v, flops, nodes, hit = host_api.contract_cached(gq, os.path.join(GOLDEN, rec["measure"]), go, True)
         assert abs(v - complex(*rec["value"])) <= 1e-10 and flops == rec["flops"]
+
+
+@pytest.mark.parametrize("csize", [3, 8])
+@pytest.mark.parametrize("name", ["qft8_X8", "qaoa20_node1_m125", "qaoa20_node5_m125", "ghz64_zeros", "two_pairs_0011", "rand20_cn3_d12_zeros"])
+def test_grouped_micro_steps_on_thread_block_clusters(built, name, csize, tmp_path):
+    """QTB_MICRO_CLUSTER=c forces EVERY grouped launch onto a thread-block cluster of c CTAs that share each level's items and meet
+    in a cluster barrier between levels (kernels.cuh; by default only heavy groups take that path -- the micro-steps of a config-2
+    term, p=2 QAOA terms).  Same value, same plan, same unit count as the reference."""
+    rec, out = _run(name, tmp_path, extra_env={"QTB_MICRO_CLUSTER": str(csize)})
+    val = complex(float(out["value"][0]), float(out["value"][1]))
+    assert _close(val, rec["value"]), (val, rec["value"])
+    assert out["plan"] == rec["plan"] and int(out["flops"][0]) == rec["flops"]
