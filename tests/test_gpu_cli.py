@@ -81,6 +81,31 @@ def test_maxcut_cli_improves_objective(built, tmp_path):
     assert len(angles) == 2
 
 
+@pytest.mark.parametrize("qasm,measure,ordering", [("Samples/qft8.qasm", "Samples/measureSampleOne.txt", "qft8_X8.qbb.out"),
+                                                  ("Samples/test_JW.qasm", "Samples/measureSampleOne.txt", "testJW_XXXX.qbb.out"),
+                                                  ("Samples/4regRand20Node5-p1.qasm", "Samples/measure125.txt", "qaoa20_node5_m125.qbb.out")])
+def test_minimal_shim_inside_the_reference_sources(built, tmp_path, qasm, measure, ordering):
+    """oracle/_ref/qtorch_shim = the reference's UNMODIFIED main.cpp and headers with the body of ONE function, Network::ContractIndices
+    (/root/reference/src/Network.h:876-971), replaced by calls on the C ABI (oracle/shim/contract_indices_body.inc, patched in a scratch
+    copy by oracle/make_shim.py) -- the minimal binding INTEGRATION.md describes.  Same script, same frozen ordering: the result file
+    must read like the unmodified reference binary's (same unit count text, value within 1e-10)."""
+    shim = os.path.join(ROOT, "oracle", "_ref", "qtorch_shim")
+    if not os.path.exists(shim) or not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/qtorch_shim / qtorch_ref not built (needs the reference tree at build time)")
+    work = _workdir(tmp_path, ordering)
+    env = dict(os.environ)
+    mine = subprocess.run([shim, _script(work, "shim", qasm, measure)], cwd=work, capture_output=True, text=True, timeout=300, env=env)
+    ref = subprocess.run([REF_CLI, _script(work, "ref", qasm, measure)], cwd=work, capture_output=True, text=True, timeout=300, env=env)
+    assert mine.returncode == 0 and ref.returncode == 0, (mine.stdout[-800:], mine.stderr[-800:], ref.stdout[-300:])
+    a, b = _result_lines(os.path.join(work, "shim.out")), _result_lines(os.path.join(work, "ref.out"))
+    assert len(a) == 2 and len(b) == 2 and a[1] == b[1], (a, b)
+
+    def value(line):
+        re_, im_ = line[len("Result of Contraction: ("):-1].split(",")
+        return complex(float(re_), float(im_))
+    assert abs(value(a[0]) - value(b[0])) <= 1e-10
+
+
 @pytest.mark.parametrize("case", ["prism6_p1", "cube8_p1", "prism6_p2"])
 def test_maxcut_cli_follows_the_reference_cobyla_trajectory(built, tmp_path, case):
     """maxcutQAOA mode 0 links the NLopt the reference vendors and makes the reference's optimiser call (LN_COBYLA from the same start,
