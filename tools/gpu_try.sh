@@ -2,6 +2,6 @@
 # tools/gpu_try.sh -- scratch: whatever is being tried on the GPU box right now
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-CS=/usr/local/cuda/bin/compute-sanitizer
-( echo "== memcheck, default kernels"; timeout 400 $CS --tool memcheck --print-limit 5 python tools/sanitize_small.py 2>&1 | tail -16
-  echo "== memcheck, QTB_GETT_C1=5 QTB_MICRO_CLUSTER=4"; QTB_GETT_C1=5 QTB_MICRO_CLUSTER=4 timeout 400 $CS --tool memcheck --print-limit 5 python tools/sanitize_small.py 2>&1 | tail -16 ) | tee gpurun_out/sanitizer.txt
+timeout 400 python -m pytest tests/test_maxcut.py tests/test_gpu_networks.py -x -q -m gpu --timeout 200 -k "maxcut or qaoa or clusters or config2" 2>&1 | tail -3
+timeout 100 python tools/prof_maxcut.py 2>&1 | tail -2
+timeout 100 python tools/prof_micro.py qaoa30_z27z29 3 | tail -1
