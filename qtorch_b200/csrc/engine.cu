@@ -1044,7 +1044,14 @@ static int launch_micro_plans(qtb_ctx *ctx, int n, long long unitsTotal, const u
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = (unsigned)c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = c > 1 ? 1 : 0;
-    CU(cudaLaunchKernelEx(&cfg, k_micro_batch, blobBase, blobAddrDev));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_micro_batch, blobBase, blobAddrDev);
+    if (e != cudaSuccess && c > 1) {
+        // a cluster that cannot be scheduled after all (the occupancy query is advisory): one CTA per plan always can
+        cudaGetLastError();
+        cfg.gridDim = dim3((unsigned)n); cfg.numAttrs = 0;
+        e = cudaLaunchKernelEx(&cfg, k_micro_batch, blobBase, blobAddrDev);
+    }
+    CU(e);
     return QTB_OK;
 }
 // one grouped launch of a single plan segment / eager group: a long chain of tiny steps stays on one CTA of 1024 threads (GHZ-1000:

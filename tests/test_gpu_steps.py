@@ -438,3 +438,16 @@ def test_shared_sum_tile_kernel_matches_the_oracle():
         r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_g3.py"), "--parity-only"], capture_output=True, text=True, timeout=600,
                            env=dict(os.environ, QTB_GETT_C1="5", QTB_G3=g3, QTORCH_QUIET="1"))
         assert r.returncode == 0 and "parity failures: 0" in r.stdout and "WRONG" not in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
+
+
+@pytest.mark.gpu
+def test_programmatic_dependent_launch_of_the_tile_kernel():
+    """QTB_PDL=1: k_gett launches carry cudaLaunchAttributeProgrammaticStreamSerialization and the kernel's griddepcontrol.wait holds
+    its first global access back until the previous grid has completed (gett.cuh).  Opt-in (measured neutral); back-to-back dependent
+    tile-kernel steps -- plain and fused -- must still match the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_g3.py"), "--parity-only"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, QTB_PDL="1", QTORCH_QUIET="1"))
+    assert r.returncode == 0 and "parity failures: 0" in r.stdout and "WRONG" not in r.stdout, (r.stdout[-800:], r.stderr[-1500:])
