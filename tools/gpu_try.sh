@@ -2,4 +2,6 @@
 # tools/gpu_try.sh -- scratch: whatever is being tried on the GPU box right now
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-timeout 400 python -m pytest tests/test_gpu_steps.py tests/test_maxcut.py -x -q -m gpu --timeout 200 -k "programmatic or maxcut or qaoa" 2>&1 | tail -3
+NCU=/usr/local/cuda/bin/ncu
+timeout 600 $NCU --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+wc -l gpurun_out/launches.csv
