@@ -2,6 +2,4 @@
 # tools/gpu_try.sh -- scratch: whatever is being tried on the GPU box right now
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-NCU=/usr/local/cuda/bin/ncu
-timeout 600 $NCU --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-wc -l gpurun_out/launches.csv
+QTB_MICRO_CLUSTER=4 timeout 420 python -m pytest tests -x -q -m gpu --timeout 200 --deselect tests/test_gpu_networks.py::test_reference_test_suite_drop_in 2>&1 | tail -5 | tee gpurun_out/pytest_cluster4.log
