@@ -362,10 +362,11 @@ def main():
     K2 = max(20, K)
 
     def sliced_run(rec, label):
-        """SlicedContraction (host/Slicing.h): as few cut wires as give every rank a slice, but at least one; slices dealt
-        round-robin; per amplitude: [stage] -> begin -> end, two amplitudes in flight, ONE in-stream allreduce each."""
+        """SlicedContraction (host/Slicing.h): as few cut wires as give every rank TWO slices (its two plan lanes then always have
+        a big launch queued behind the running one), at least one wire; slices dealt round-robin; per amplitude: [stage] -> begin ->
+        end, two amplitudes in flight, ONE in-stream allreduce each."""
         s_wires = 1
-        while 4 ** s_wires < world:
+        while 4 ** s_wires < 2 * world:
             s_wires += 1
         paths = [os.path.join(GOLDEN, rec[k]) for k in ("qasm", "measure", "ordering")]
         net = host_api.SlicedNetwork(*paths, True, slice_wires=s_wires, lanes=2, rank=rank, world=world)
