@@ -17,7 +17,7 @@
 //     (re, im) fragments and has no FP64 add left.  A sum tile is stored fragment-native ([block][k-step][lane][i]), so
 //     writer and readers use the same lane and no index arithmetic.  (Letting the PRODUCER warpgroup form the sums was
 //     measured first and dropped: a DADD issued by a fifth warp queues ~325 cycles behind the math warps' DMMAs, the sums
-//     arrive late: 3.79-3.93 ms against 3.52, profiles/r02_g3_producer_sums.txt.)
+//     arrive late: 3.79-3.93 ms against 3.52, profiles/r02_g3_shared_sums.txt.)
 //   * ordering: a warp multiplies slot q after `summed[q % 3]` completes, i.e. after all 16 warps have started slot q - 1;
 //     the tile written at slot q (for q + 1) was last read at slot q - 2, which every warp has left by then.
 //   * operand tiles are unpadded and XOR-swizzled (32 KB per stage instead of 40 KB), which is what makes room for three sum
