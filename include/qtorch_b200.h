@@ -158,7 +158,8 @@ long long qtb_sliced_prefix_units(qtb_sliced *sliced);
 int qtb_sliced_launches(qtb_sliced *sliced, int *prefix_launches);   /* kernel launches of one slice (prefix included) */
 /* Grouped evaluation of n independent plans with scalar outputs (e.g. the 45 per-edge <ZiZj> networks of one QAOA
  * objective evaluation, maxcut.cpp:171-198): all inputs are uploaded, plans that consist of micro-steps only run in
- * ONE launch (one CTA per plan), the n scalars come back with one synchronisation.
+ * ONE launch (one CTA -- or, for heavy plans when SMs are free, one thread-block cluster -- per plan), the n scalars come
+ * back with one synchronisation.
  * host_inputs[i] is plan i's array of input pointers; host_out receives n (re, im) pairs.                       */
 int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const double *const *const *host_inputs, double *host_out);
 /* Term batches: n independent scalar plans whose inputs stay resident in HBM and of which only a few small gate tensors
@@ -166,7 +167,8 @@ int qtb_plans_run_batched(qtb_ctx *ctx, qtb_plan *const *plans, int n, const dou
  * qtb_batch_set_inputs uploads a plan's inputs once; qtb_batch_bind declares that input `input` of plan `plan` is table
  * `table` of the per-evaluation table set (n_tables tensors of rank table_rank, e.g. Rz(-gamma_l) and Rx(2 beta_l)).
  * One evaluation = one CUDA-graph launch: H2D of the tables (n_tables * 16 * 4^table_rank bytes), scatter into the bound
- * inputs, all plans (one CTA per plan when they are grouped micro-steps only, forked streams otherwise), gather of the n
+ * inputs, all plans (one CTA or one thread-block cluster per plan when they are grouped micro-steps only, forked streams
+ * otherwise), gather of the n
  * scalars and their sum in a fixed order, optionally ONE in-stream ncclAllReduce of the sum (replaces f_pVal += ...,
  * maxcut.cpp:196), one D2H.  begin returns at once; end waits and returns the sum (over all ranks after an allreduce) and,
  * if `terms` is not NULL, this rank's n individual (re, im) pairs.                                                      */
