@@ -765,6 +765,22 @@ static bool micro_timeline_enabled() {
 
 static int launch_micro_group(qtb_ctx *ctx, const uint8_t *blobBase, const uint64_t *offsetDev, long long units, cudaStream_t s);
 
+// Lane layout of one micro-step (k_micro): 2^lg lanes share an output along the summed index, P = 32 >> lg outputs per pass,
+// 2^lp <= 4 passes per item; returns the serial multiply-add chain of one lane, 2^lp * max(1, K >> lg).  G is at least 32 / NC
+// (tiny results still use the whole warp); passes shrink first and then G grows while the chain is longer than `target`.
+static uint32_t micro_item_layout(uint32_t NC, uint32_t K, uint32_t target, uint32_t &lg, uint32_t &lp) {
+    lg = 0; lp = 2;
+    while ((32u >> lg) > NC) lg++;                                    // P = 32 / G <= NC
+    while (lp > 0 && ((32u >> lg) << lp) > NC) lp--;                  // passes * P <= NC
+    auto serialOf = [&](uint32_t l, uint32_t q) { return (1u << q) * std::max<uint32_t>(1u, K >> l); };
+    while (serialOf(lg, lp) > target) {                               // fewer passes first (more items, same lanes per output)
+        if (lp > 0) lp--;
+        else if (lg < 5 && (2u << lg) <= K) lg++;
+        else break;
+    }
+    return serialOf(lg, lp);
+}
+
 // ---- micro-batch blob assembly -----------------------------------------------------------------
 // Builds: MicroHeader | levelItemStart | items | steps (copy steps first at level 0) | payload
 static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std::vector<PendingUpload> &ups,
@@ -800,16 +816,10 @@ static size_t build_micro_blob(const std::vector<PendingStep> &steps, const std:
     for (const auto &s : steps) {
         all[idx] = s.st;
         const uint32_t NC = 1u << (2 * s.st.rC), K = 1u << (2 * s.st.k);
-        uint32_t lg = 0, lp = 2;                                          // lanes per output 2^lg, passes per item 2^lp
-        while ((32u >> lg) > NC) lg++;                                    // P = 32 / G <= NC
-        while (lp > 0 && ((32u >> lg) << lp) > NC) lp--;                  // passes * P <= NC
+        uint32_t lg, lp;
         const uint32_t target = (uint32_t)std::max(16.0, levelWork[s.level] / (QTB_MICRO_THREADS / 32));
-        auto serialOf = [&](uint32_t l, uint32_t q) { return (1u << q) * std::max<uint32_t>(1u, K >> l); };
-        while (serialOf(lg, lp) > target) {                               // fewer passes first (more items, same lanes per output)
-            if (lp > 0) lp--;
-            else if (lg < 5 && (2u << lg) <= K) { lg++; }
-            else break;
-        }
+        const uint32_t itemSerial = micro_item_layout(NC, K, target, lg, lp);
+        auto serialOf = [&](uint32_t, uint32_t) { return itemSerial; };
         const uint32_t perItem = (32u >> lg) << lp;                       // outputs of one item
         const uint32_t nChunks = NC / perItem;
         for (uint32_t c = 0; c < nChunks; c++) sorted[s.level].push_back({serialOf(lg, lp), {idx, c | (lg << 24) | (lp << 29)}});
@@ -1366,7 +1376,15 @@ int qtb_contract(qtb_ctx *ctx, qtb_tensor a, qtb_tensor b, int k, const int *pos
     return QTB_OK;
 }
 
-// debugging aid (not part of the public header): prints the clock stamps the grouped launches of compiled plans left behind
+// debugging aids (not part of the public header)
+int qtb_debug_micro_layout(int rC, int k, int target, int *lg, int *lp) {          // tests/test_abi.py checks its invariants on the CPU
+    uint32_t a = 0, b = 0;
+    const uint32_t serial = micro_item_layout(1u << (2 * rC), 1u << (2 * k), (uint32_t)target, a, b);
+    if (lg) *lg = (int)a;
+    if (lp) *lp = (int)b;
+    return (int)serial;
+}
+// prints the clock stamps the grouped launches of compiled plans left behind
 int qtb_debug_dump_micro_timelines(int maxBlobs) {
     cudaDeviceSynchronize();
     int n = 0;

@@ -55,3 +55,30 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".h", ".hpp", ".cu", ".cuh", ".cpp", ".inl")):
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert "contract_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_micro_step_lane_layout_invariants(built):
+    """host logic of the grouped micro-step executor (engine.cu micro_item_layout): for every step shape and every target chain
+    length the layout must tile the outputs exactly (items x passes x outputs-per-pass = 4^rC), use whole warps, never put more
+    lanes on an output than there are summed terms unless the result itself is smaller than a warp, and return the chain length
+    the kernel will really run."""
+    L = qt.load_library()
+    L.qtb_debug_micro_layout.restype = ctypes.c_int
+    L.qtb_debug_micro_layout.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    for rC in range(0, 8):
+        for k in range(0, 9):
+            NC, K = 4 ** rC, 4 ** k
+            prev = None
+            for target in (1, 4, 16, 64, 256, 4096, 10 ** 6):
+                lg, lp = ctypes.c_int(), ctypes.c_int()
+                serial = L.qtb_debug_micro_layout(rC, k, target, ctypes.byref(lg), ctypes.byref(lp))
+                G, P, passes = 1 << lg.value, 32 >> lg.value, 1 << lp.value
+                assert 0 <= lg.value <= 5 and 0 <= lp.value <= 2
+                assert P <= NC or NC < 32 and P == NC, (rC, k, target, lg.value)
+                assert P * passes <= NC and NC % (P * passes) == 0
+                assert G <= max(K, 32 // min(NC, 32)), (rC, k, target, G)          # more lanes than terms only to fill a warp
+                assert serial == passes * max(1, K >> lg.value)
+                if prev is not None:
+                    assert serial >= prev                                          # a looser target never shortens the chain
+                prev = serial
+            assert prev == min(4, max(1, NC // min(NC, 32))) * max(1, K >> max(0, 5 - min(5, 2 * rC)))   # no pressure: 4 passes (or all outputs), G = 32 / NC at most

@@ -2,4 +2,5 @@
 # tools/gpu_try.sh -- scratch: whatever is being tried on the GPU box right now
 mkdir -p gpurun_out
 export QTORCH_QUIET=1
-QTB_MICRO_CLUSTER=4 timeout 420 python -m pytest tests -x -q -m gpu --timeout 200 --deselect tests/test_gpu_networks.py::test_reference_test_suite_drop_in 2>&1 | tail -5 | tee gpurun_out/pytest_cluster4.log
+timeout 300 python -m pytest tests/test_gpu_steps.py tests/test_maxcut.py tests/test_gpu_networks.py -x -q -m gpu --timeout 200 -k "micro or maxcut or qaoa or clusters or ghz or qft" 2>&1 | tail -2
+timeout 100 python tools/prof_maxcut.py 2>&1 | tail -2 | cut -c1-20,100-220
