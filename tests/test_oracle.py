@@ -76,3 +76,24 @@ def test_oracle_vs_live_reference(built):
             Cr, out = O.ref_step(A, rA, B, rB, pA, pB, d)
         C = O.contract(A, rA, B, rB, pA, pB)
         assert np.array_equal(C.view(np.float64), Cr.view(np.float64))
+
+
+def test_shim_patcher_replaces_exactly_one_function_body():
+    """oracle/make_shim.py (the minimal shim of INTEGRATION.md) cuts the body of Network::ContractIndices out of the reference header
+    by brace matching: nested blocks inside the body go, the declaration in the class and every other function stay."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_shim", os.path.join(os.path.dirname(O.__file__), "make_shim.py"))
+    ms = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ms)
+    header = (
+        "#pragma once\n#include <vector>\nclass Network {\n    inline void ContractIndices(int a, std::shared_ptr<Node> nodeC);\n};\n"
+        "inline void Network::Other() { if (x) { y(); } }\n"
+        "    inline void Network::ContractIndices(int a,\n            std::shared_ptr<Node> nodeC) {\n"
+        "        auto f1 = [&]() { for (;;) { if (a) { break; } } };\n        if (a) { f1(); } else { g(); }\n    }\n"
+        "inline void Network::After() { z(); }\n")
+    out = ms.patched_network_h(header, "        BODY();")
+    assert out.count("BODY();") == 1 and "f1" not in out and "g();" not in out
+    assert "inline void Network::Other() { if (x) { y(); } }" in out and "inline void Network::After() { z(); }" in out
+    assert "inline void ContractIndices(int a, std::shared_ptr<Node> nodeC);" in out            # the in-class declaration is untouched
+    assert out.index('#include "qtorch_b200.h"') < out.index("#include <vector>")
+    assert out.count("{") == out.count("}")
